@@ -1,0 +1,194 @@
+/*
+ * camcal_b200.h -- C ABI of libcamcal_b200.so: the B200 (sm_100a) implementation of
+ * the calibration-object evaluation path of yakir12/CameraCalibrations v0.7.3.
+ *
+ * The reference has no FFI of its own; its boundary is the Julia callable surface of
+ * `Calibration` (src/meta.jl:82-103) and the bulk callers in
+ * src/buildcalibrations.jl:28-67 and src/plot_calibration.jl:15-22,40.  Each entry
+ * point below names the reference lines it replaces.  A Julia wrapper binds these
+ * with `ccall` (see INTEGRATION.md and julia/CameraCalibrationsB200.jl); the Python
+ * package cameracalibrations_b200 binds the same symbols with ctypes.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 (CC_OK) or a negative cc_status and
+ *    never throws; cc_last_error_string() gives the text for the calling thread.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *    with CC_ERR_NO_DEVICE.
+ *  - `*_f64` / `*_f32`, `rectify_*`, `reproj_*` take DEVICE pointers and are
+ *    asynchronous on `stream` (a cudaStream_t passed as void*, NULL = default
+ *    stream); `*_host` variants take HOST pointers, run a chunked
+ *    H2D -> kernel -> D2H pipeline and return when the result is in host memory.
+ *  - point sets are SoA (one array per coordinate).  Pointers aligned to 16 bytes
+ *    take the 128-bit vector path; unaligned pointers are accepted (scalar path).
+ *  - frames are stored the way Julia stores `img[r, c]` (size (sz1, sz2)): pixel
+ *    (r, c), 1-based, lives at  base + (c-1)*pitch + (r-1)  in PIXELS; the first
+ *    RowCol component `r` is the contiguous axis.  Frame f of a batch
+ *    starts frame_stride pixels after frame f-1.  u8c3 pixels are 3 interleaved
+ *    bytes (RGB{N0f8}).
+ *  - parameters are passed by value in host structs (cc_intr, cc_view); the library
+ *    expands the rotation vector and the inverse maps once per call on the host,
+ *    exactly what `Calibration(...)` / `img2obj` precompute (src/meta.jl:27-33,71-76).
+ */
+#ifndef CAMCAL_B200_H
+#define CAMCAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_ABI_VERSION 1
+
+typedef enum {
+    CC_OK = 0,
+    CC_ERR_INVALID_ARG = -1,  /* NULL pointer, non-positive size, bad flag          */
+    CC_ERR_NO_DEVICE = -2,    /* no CUDA device / driver: there is no CPU fallback  */
+    CC_ERR_CUDA = -3,         /* a CUDA runtime call failed (text in last error)    */
+    CC_ERR_UNSUPPORTED = -4,  /* device is not sm_100                               */
+    CC_ERR_NOMEM = -5
+} cc_status;
+
+/* Calibration.intrinsic (AffineMap diag + translation), Calibration.k and the
+ * checker_size behind Calibration.scale -- src/meta.jl:17-25,
+ * src/buildcalibrations.jl:1-6. */
+typedef struct {
+    double frow, fcol, crow, ccol, k, checker_size;
+} cc_intr;
+
+/* Calibration.extrinsics[i]: RotationVec + translation -- src/buildcalibrations.jl:3 */
+typedef struct {
+    double rvec[3], tvec[3];
+} cc_view;
+
+typedef struct cc_ctx cc_ctx; /* per-device scratch, staging buffers, streams */
+
+/* coordinate arithmetic of the rectification map */
+#define CC_COORD_F64 0u     /* reference precision: bit-exact index/weight selection  */
+#define CC_COORD_F32 1u     /* fast path: map within 1e-3 px of the FP64 map          */
+/* how source texels are fetched */
+#define CC_GATHER_AUTO 0u   /* TMA-staged tiles when the frame layout allows, else direct */
+#define CC_GATHER_DIRECT 16u
+#define CC_GATHER_TMA 32u   /* fail with CC_ERR_INVALID_ARG if the layout cannot be staged */
+
+int cc_abi_version(void);
+const char *cc_last_error_string(void);
+int cc_device_count(int *count);
+
+int cc_ctx_create(int device, cc_ctx **out);
+int cc_ctx_destroy(cc_ctx *ctx);
+int cc_ctx_device(const cc_ctx *ctx, int *device);
+int cc_ctx_synchronize(cc_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int cc_ctx_launch_count(const cc_ctx *ctx, uint64_t *count);
+
+/* pinned host memory for the *_host entry points (optional; pageable works, slower) */
+int cc_host_alloc(void **ptr, size_t bytes);
+int cc_host_free(void *ptr);
+int cc_host_register(void *ptr, size_t bytes);
+int cc_host_unregister(void *ptr);
+
+/* ---- pixel -> world:  (c::Calibration)(i::RowCol, idx)  src/meta.jl:82, chain :31,
+ *      inv_lens_distortion :50-57, get_inv_prespective_map :60-69, img2obj :71-76.
+ *      z == NULL gives rectification(c, idx) = pop o image2real  (src/meta.jl:99-103).
+ *      Bulk form of the broadcast c.(imgpoints, i), src/buildcalibrations.jl:46. */
+int cc_img2world_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                     const double *row, const double *col, double *x, double *y,
+                     double *z, size_t n, void *stream);
+int cc_img2world_f32(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                     const float *row, const float *col, float *x, float *y, float *z,
+                     size_t n, void *stream);
+int cc_img2world_f64_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                          const double *row, const double *col, double *x, double *y,
+                          double *z, size_t n);
+int cc_img2world_f32_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                          const float *row, const float *col, float *x, float *y,
+                          float *z, size_t n);
+
+/* ---- world -> pixel:  (c::Calibration)(xyz::XYZ, idx)  src/meta.jl:88, chain :29,
+ *      lens_distortion :39-44.  z == NULL means z = 0 (points on the board plane).
+ *      Bulk form of c.(objpoints, i), src/buildcalibrations.jl:29. */
+int cc_world2img_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                     const double *x, const double *y, const double *z, double *row,
+                     double *col, size_t n, void *stream);
+int cc_world2img_f32(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                     const float *x, const float *y, const float *z, float *row,
+                     float *col, size_t n, void *stream);
+int cc_world2img_f64_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                          const double *x, const double *y, const double *z,
+                          double *row, double *col, size_t n);
+int cc_world2img_f32_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                          const float *x, const float *y, const float *z, float *row,
+                          float *col, size_t n);
+
+/* ---- full-frame rectification:  warp(img, tform, axs)  src/plot_calibration.jl:40
+ *      with tform = real2image[i] o push(.,0) o inv(LinearMap(ratio*I)) (:17-18) and
+ *      axs from get_axes (:1-6): output index (I1, I2) = axs_min + (a, b), same size
+ *      as the input.  Bilinear, OnGrid, out-of-range -> fill.  `ratio` is pixels per
+ *      world unit (get_ratio, :8-13).  flags = CC_COORD_* | CC_GATHER_*. */
+int cc_rectify_f32c1(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, double ratio,
+                     const int64_t axs_min[2], const float *src, float *dst, int sz1,
+                     int sz2, size_t pitch, size_t frame_stride, int nframes, float fill,
+                     unsigned flags, void *stream);
+int cc_rectify_u8c3(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, double ratio,
+                    const int64_t axs_min[2], const uint8_t *src, uint8_t *dst, int sz1,
+                    int sz2, size_t pitch, size_t frame_stride, int nframes,
+                    const uint8_t fill[3], unsigned flags, void *stream);
+int cc_rectify_f32c1_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                          double ratio, const int64_t axs_min[2], const float *src,
+                          float *dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
+                          int nframes, float fill, unsigned flags);
+int cc_rectify_u8c3_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
+                         double ratio, const int64_t axs_min[2], const uint8_t *src,
+                         uint8_t *dst, int sz1, int sz2, size_t pitch,
+                         size_t frame_stride, int nframes, const uint8_t fill[3],
+                         unsigned flags);
+/* the map alone (source row/col sampled by each output pixel), FP64, frame layout */
+int cc_rectify_map_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, double ratio,
+                       const int64_t axs_min[2], double *map_row, double *map_col, int sz1,
+                       int sz2, size_t pitch, void *stream);
+
+/* get_ratio / get_axes (src/plot_calibration.jl:1-13): tiny host-side helpers so a
+ * binding needs nothing else to drive cc_rectify_*.  corners: (a, b) at [a + n1*b]. */
+int cc_get_ratio(const double *rows, const double *cols, int n1, int n2,
+                 double checker_size, double *ratio);
+int cc_get_axes(double ratio, double checker_size, int n1, int n2, int sz1, int sz2,
+                int64_t axs_min[2]);
+
+/* ---- reprojection residual + Jacobian + normal-equation blocks.
+ *      Residual: _reprojection, src/buildcalibrations.jl:28-31.  Jacobian / J'J: the
+ *      arithmetic OpenCV.calibrateCamera reduces for the flags of src/detect_fit.jl:40
+ *      (ZERO_TANGENT + FIX_K2 + FIX_K3 + FIX_ASPECT_RATIO); free parameters per view
+ *      e = (rvec, tvec), shared i = (f, crow, ccol, k) with frow = aspect*f, fcol = f.
+ *        views    device, nviews cc_view
+ *        obj      device, ncorners x 3 (x,y,z interleaved; shared by all views)
+ *        img      device, nviews x ncorners x 2 (row,col interleaved)
+ *        per_view device, nviews x 66: [JtJ_ee 6x6 | JtJ_ei 6x4 | Jtr_e 6]
+ *        shared   device, 21: [JtJ_ii 4x4 | Jtr_i 4 | sum r^2]  (this device's views;
+ *                 all-reduce it across ranks with NCCL -- the host layer does that)
+ *      The reduction order is fixed: results are bit-reproducible run to run. */
+#define CC_PER_VIEW 66
+#define CC_SHARED 21
+int cc_reproj_jtj_f64(cc_ctx *ctx, const cc_intr *intr, double aspect, const cc_view *views,
+                      int nviews, const double *obj, const double *img, int ncorners,
+                      double *per_view, double *shared, void *stream);
+int cc_reproj_jtj_f64_host(cc_ctx *ctx, const cc_intr *intr, double aspect,
+                           const cc_view *views, int nviews, const double *obj,
+                           const double *img, int ncorners, double *per_view,
+                           double *shared);
+
+/* ---- calculate_errors, src/buildcalibrations.jl:37-67, fused on the device.
+ *        n1 x n2 corners per view (a fastest); inv_rows/inv_cols: nviews x
+ *        inverse_samples pre-drawn pixels in [1, sz] (the reference draws rand());
+ *        sums (device, 4): raw sums {reprojection, projection, distance, inverse}
+ *        before the RMS normalisation (all-reduce, then normalise on the host). */
+int cc_calculate_errors_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *views,
+                            int nviews, const double *obj, const double *img, int n1, int n2,
+                            const double *inv_rows, const double *inv_cols,
+                            int inverse_samples, double *sums, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances (BASELINE.json north_star):
+  FP64 kernels            <= 1e-9 px / world units
+  FP32 fast path          <= 1e-3 px (round trip / map error)
+  FP64 remap              bit-exact map, indices, weights and output
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from conftest import BENCH_VIEW, C2_INTR, C3_INTR, SYN_VIEW, camera_for, load_golden
+from oracle import oracle_c as oc
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+TOL32_PX = 1e-3
+
+
+@pytest.fixture(scope="module")
+def cc():
+    import cameracalibrations_b200 as m
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m.context(0)  # raises if the extension cannot run: no fallback
+    return m
+
+
+def _calib(cc, intr, views, files=None):
+    files = files or [f"{i}.png" for i in range(len(views))]
+    return cc.Calibration(intr[:4], views, 1.0 / intr[5], intr[4], files)
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ------------------------------------------------------------------ point maps
+def test_config1_every_pixel_round_trip(cc, example_fit):
+    """BASELINE config 1: c(RowCol,1) <-> c(xyz,1) over every pixel of one 375x500 frame."""
+    intr = example_fit["intr_tuple"]
+    c = _calib(cc, intr, example_fit["view_list"], example_fit["files"])
+    sz1, sz2 = example_fit["sz"]
+    r, q = np.meshgrid(np.arange(1, sz1 + 1, dtype=np.float64), np.arange(1, sz2 + 1, dtype=np.float64),
+                       indexing="ij")
+    r, q = r.ravel(), q.ravel()
+    for vi, (rv, tv) in enumerate(example_fit["view_list"]):
+        ch = oc.chain(intr, rv, tv)
+        ox, oy, oz = oc.img2world_soa(ch, r, q)
+        x, y, z = c.img2world(_dev(r), _dev(q), vi)
+        for got, ref in ((x, ox), (y, oy), (z, oz)):
+            assert np.max(np.abs(got.cpu().numpy() - ref)) <= TOL64
+        row, col = c.world2img(x, y, z, vi)
+        assert np.max(np.abs(row.cpu().numpy() - r)) <= TOL64
+        assert np.max(np.abs(col.cpu().numpy() - q)) <= TOL64
+        # the AoS callable of the reference: (n,2) -> (n,3) -> (n,2)
+        pts = torch.stack([_dev(r[:1000]), _dev(q[:1000])], dim=-1)
+        back = c(c(pts, vi), vi)
+        assert torch.max(torch.abs(back - pts)).item() <= TOL64
+
+
+def test_reference_rectification_identity(cc, example_fit):
+    """test/runtests.jl:79-85: rectification(c,1)(RowCol(1,2)) == c(RowCol(1,2),1)[[1,2]] (exact)."""
+    c = _calib(cc, example_fit["intr_tuple"], example_fit["view_list"], example_fit["files"])
+    i = torch.tensor([[1.0, 2.0]], dtype=torch.float64, device="cuda")
+    f = cc.rectification(c, 0)
+    assert torch.equal(f(i), c(i, 0)[:, :2])
+    # host path, same identity and same numbers
+    ih = np.array([[1.0, 2.0]])
+    assert np.array_equal(cc.rectification(c, 0)(ih), c(ih, 0)[:, :2])
+    assert np.array_equal(c(ih, 0), c(i, 0).cpu().numpy())
+    # SURVEY Appendix A known answer
+    assert abs(c(ih, 0)[0, 0] - (-0.709323329459491)) < 1e-12
+
+
+@pytest.mark.parametrize("k", [-0.12, 0.0, 0.056417832172007555, 0.9])
+def test_img2world_f64_random_points(cc, k):
+    intr = C3_INTR[:4] + (k, 2.5)
+    c = _calib(cc, intr, [SYN_VIEW])
+    ch = oc.chain(intr, *SYN_VIEW)
+    rng = np.random.default_rng(99)
+    n = 1_000_003  # odd: exercises the scalar tail
+    row, col = rng.uniform(0, 2160, n), rng.uniform(0, 3840, n)
+    ox, oy, oz = oc.img2world_soa(ch, row, col)
+    x, y, z = c.img2world(_dev(row), _dev(col), 0)
+    scale = max(1.0, float(np.max(np.abs(ox))), float(np.max(np.abs(oy))))
+    for got, ref in ((x, ox), (y, oy), (z, oz)):
+        assert np.max(np.abs(got.cpu().numpy() - ref)) <= TOL64 * scale
+    # rectification variant (z == NULL) gives the same x, y bit for bit
+    x2, y2 = c.img2world(_dev(row), _dev(col), 0, want_z=False)
+    assert torch.equal(x2, x) and torch.equal(y2, y)
+    # unaligned views take the scalar path: same bits
+    x3, y3, z3 = c.img2world(_dev(row)[1:], _dev(col)[1:], 0)
+    assert torch.equal(x3, x[1:]) and torch.equal(z3, z[1:])
+    # world -> pixel is the same operation order as the oracle: bit-exact
+    orow, ocol = oc.world2img_soa(ch, ox, oy, oz)
+    r2, c2 = c.world2img(_dev(ox), _dev(oy), _dev(oz), 0)
+    assert np.array_equal(r2.cpu().numpy(), orow) and np.array_equal(c2.cpu().numpy(), ocol)
+    assert np.max(np.abs(orow - row)) < 1e-8
+
+
+def test_inverse_distortion_branches(cc):
+    """c == 0, c > 0 large, -4/27 < c < 0 up to the double root, c < -4/27 (negative root)."""
+    intr = (1.0, 1.0, 0.0, 0.0, 1.0, 1.0)   # u = row, v = col, k = 1  ->  c = row^2 + col^2
+    view = ((0.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+    cs = np.concatenate([[0.0, 1e-300, 1e-12, 40.0, 1e3], np.linspace(1e-6, 8, 500)])
+    row = np.sqrt(cs)
+    col = np.zeros_like(row)
+    c = _calib(cc, intr, [view])
+    x, y, z = c.img2world(_dev(row), _dev(col), 0)
+    ox, oy, oz = oc.img2world_soa(oc.chain(intr, *view), row, col)
+    assert np.max(np.abs(x.cpu().numpy() - ox)) <= TOL64
+    # negative k: c = -r^2
+    intr = (1.0, 1.0, 0.0, 0.0, -1.0, 1.0)
+    cneg = np.concatenate([np.linspace(1e-6, 0.148, 400), np.linspace(0.1485, 3.0, 200)])
+    row = np.sqrt(cneg)
+    col = np.zeros_like(row)
+    c = _calib(cc, intr, [view])
+    x, y, z = c.img2world(_dev(row), _dev(col), 0)
+    ox, oy, oz = oc.img2world_soa(oc.chain(intr, *view), row, col)
+    near = np.abs(cneg - 4 / 27) < 2e-3      # double root: conditioning ~ 1/sqrt(distance)
+    assert np.max(np.abs(x.cpu().numpy() - ox)[~near]) <= TOL64
+    assert np.max(np.abs(x.cpu().numpy() - ox)[near]) <= 1e-6
+    assert np.all(x.cpu().numpy()[cneg > 0.1485] < 0)      # the reference divides by the negative root
+
+
+def test_f32_fast_path_round_trip(cc):
+    """FP32 kernels: world->pixel of the FP32 pixel->world result, evaluated in FP64 by the
+    oracle, lands within 1e-3 px of the input pixel (4K camera)."""
+    c = _calib(cc, C3_INTR, [SYN_VIEW])
+    ch = oc.chain(C3_INTR, *SYN_VIEW)
+    rng = np.random.default_rng(7)
+    n = 400_001
+    row = rng.uniform(0, 2160, n).astype(np.float32)
+    col = rng.uniform(0, 3840, n).astype(np.float32)
+    x, y, z = c.img2world(_dev(row), _dev(col), 0)
+    assert x.dtype == torch.float32
+    r64, c64 = oc.world2img_soa(ch, x.cpu().numpy().astype(np.float64), y.cpu().numpy().astype(np.float64),
+                                z.cpu().numpy().astype(np.float64))
+    err = np.maximum(np.abs(r64 - row), np.abs(c64 - col))
+    assert np.max(err) <= TOL32_PX, np.max(err)
+    # FP32 forward map against the FP64 oracle
+    ox, oy, oz = oc.img2world_soa(ch, row.astype(np.float64), col.astype(np.float64))
+    r32, c32 = c.world2img(_dev(ox, torch.float32), _dev(oy, torch.float32), None, 0)
+    r64, c64 = oc.world2img_soa(ch, ox.astype(np.float32).astype(np.float64),
+                                oy.astype(np.float32).astype(np.float64))
+    assert np.max(np.abs(r32.cpu().numpy() - r64)) <= TOL32_PX
+    assert np.max(np.abs(c32.cpu().numpy() - c64)) <= TOL32_PX
+
+
+def test_host_entry_points_match_device(cc):
+    c = _calib(cc, C2_INTR, [SYN_VIEW])
+    rng = np.random.default_rng(3)
+    n = (1 << 22) * 2 + 12345     # three pipeline chunks
+    row, col = rng.uniform(0, 1080, n), rng.uniform(0, 1920, n)
+    hx, hy, hz = c.img2world(row, col, 0)
+    dx, dy, dz = c.img2world(_dev(row), _dev(col), 0)
+    assert np.array_equal(hx, dx.cpu().numpy()) and np.array_equal(hz, dz.cpu().numpy())
+    hr, hc = c.world2img(hx, hy, hz, 0)
+    dr, dc = c.world2img(dx, dy, dz, 0)
+    assert np.array_equal(hr, dr.cpu().numpy()) and np.array_equal(hc, dc.cpu().numpy())
+    # empty input
+    e = np.empty(0)
+    assert c.img2world(e, e, 0)[0].size == 0
+
+
+def test_bad_arguments(cc):
+    c = _calib(cc, C2_INTR, [SYN_VIEW])
+    with pytest.raises(IndexError):
+        c.img2world(np.zeros(4), np.zeros(4), 3)          # BoundsError in the reference
+    with pytest.raises(IndexError):
+        c(np.zeros((1, 2)))                               # no file named *extrinsic*
+    c2 = _calib(cc, C2_INTR, [SYN_VIEW, SYN_VIEW], ["a.png", "my_extrinsic.png"])
+    assert c2(np.array([[5.0, 6.0]])).shape == (1, 3)     # src/meta.jl:90-93
+    with pytest.raises(cc.CamcalError):
+        cc.warp(c, 0, np.zeros((1, 8, 8), np.float32), -1.0, (0, 0))
+
+
+# ------------------------------------------------------------------ rectification
+def _rect_case(intr, sz, ratio_scale=1.0, view=SYN_VIEW):
+    n1, n2 = 20, 14
+    ch = oc.chain(intr, *view)
+    a, b = np.meshgrid(np.arange(n1, dtype=np.float64), np.arange(n2, dtype=np.float64), indexing="ij")
+    x, y = (a * intr[5]).ravel(), (b * intr[5]).ravel()
+    row, col = oc.world2img_soa(ch, x, y)
+    ip = np.stack([row, col], axis=-1).reshape(n1, n2, 2)
+    ratio = oc.get_ratio(ip, intr[5]) * ratio_scale
+    axs = oc.get_axes(ratio, intr[5], (n1, n2), sz)
+    return ch, ip, ratio, axs
+
+
+@pytest.mark.parametrize("sz", [(1080, 1920), (375, 500), (131, 77), (128, 8), (4, 3)])
+def test_rectify_f32c1_bit_exact(cc, sz):
+    intr = camera_for(sz)
+    ch, ip, ratio, axs = _rect_case(intr, sz)
+    c = _calib(cc, intr, [SYN_VIEW])
+    assert abs(cc.get_ratio(ip, intr[5]) - ratio) == 0.0
+    assert cc.get_axes(ratio, intr[5], (20, 14), sz) == axs
+    rng = np.random.default_rng(1234)
+    nf = 3 if sz[0] * sz[1] < 1_000_000 else 2
+    frames = rng.random((nf, sz[1], sz[0]), dtype=np.float32)
+    ref = oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=np.nan)
+    got = cc.warp(c, 0, _dev(frames), ratio, axs).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.array_equal(got[ok], ref[ok])               # bit-exact
+    if sz[1] >= 77:
+        assert 0.3 < ok.mean()
+    # the map itself: bit-exact source coordinates => bit-exact indices and weights
+    mr, mc = cc.rectify_map(c, 0, ratio, axs, sz)
+    omr, omc = oc.rectify_map(ch, 1.0 / ratio, axs, sz)
+    assert np.array_equal(mr.cpu().numpy(), omr) and np.array_equal(mc.cpu().numpy(), omc)
+    # host entry point, explicit fill value
+    got_h = cc.warp(c, 0, frames, ratio, axs, fill=-5.0)
+    ref_h = oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-5.0)
+    assert np.array_equal(got_h, ref_h)
+
+
+@pytest.mark.parametrize("sz", [(2160, 3840), (1080, 1920), (360, 640), (131, 77), (16, 5)])
+def test_rectify_u8c3_bit_exact(cc, sz):
+    intr = camera_for(sz)
+    ch, ip, ratio, axs = _rect_case(intr, sz)
+    c = _calib(cc, intr, [SYN_VIEW])
+    rng = np.random.default_rng(4321)
+    nf = 2 if sz[0] * sz[1] < 1_000_000 else 1
+    frames = rng.integers(0, 256, (nf, sz[1], sz[0], 3), dtype=np.uint8)
+    ref = oc.rectify_u8c3(ch, 1.0 / ratio, axs, frames, fill=(1, 2, 3))
+    got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(1, 2, 3)).cpu().numpy()
+    assert np.array_equal(got, ref)
+    got_h = cc.warp(c, 0, frames, ratio, axs, fill=(1, 2, 3))
+    assert np.array_equal(got_h, ref)
+
+
+def test_rectify_edge_rule(cc):
+    """x == n in bounds with (i, delta) = (n-1, 1); just outside -> fill; exact grid hits."""
+    intr = (1.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+    view = ((0.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+    c = _calib(cc, intr, [view])
+    img = np.arange(12, dtype=np.float32).reshape(1, 3, 4)
+    assert np.array_equal(cc.warp(c, 0, _dev(img), 1.0, (1, 1), fill=-1.0).cpu().numpy(), img)
+    out = cc.warp(c, 0, _dev(img), 1.0, (0, 1), fill=-1.0).cpu().numpy()[0]
+    assert np.all(out[:, 0] == -1.0) and np.array_equal(out[:, 1:], img[0][:, :3])
+    out = cc.warp(c, 0, _dev(img), 2.0, (2, 2), fill=-1.0).cpu().numpy()[0]
+    assert out[0, 0] == img[0, 0, 0] and out[0, 1] == 0.5 * (img[0, 0, 0] + img[0, 0, 1])
+
+
+@pytest.mark.parametrize("intr,sz", [(C2_INTR, (1080, 1920)), (C3_INTR, (2160, 3840))])
+def test_rectify_f32_coords_within_1e3_px(cc, intr, sz):
+    """FP32 fast path: warp a row-ramp and a column-ramp; bilinear interpolation reproduces a
+    ramp exactly, so the outputs ARE the FP32 map; compare with the FP64 oracle map."""
+    ch, ip, ratio, axs = _rect_case(intr, sz)
+    c = _calib(cc, intr, [SYN_VIEW])
+    r = np.arange(1, sz[0] + 1, dtype=np.float32)
+    q = np.arange(1, sz[1] + 1, dtype=np.float32)
+    frames = np.stack([np.broadcast_to(r[None, :], (sz[1], sz[0])),
+                       np.broadcast_to(q[:, None], (sz[1], sz[0]))]).astype(np.float32)
+    got = cc.warp(c, 0, _dev(frames), ratio, axs, coord="f32").cpu().numpy().astype(np.float64)
+    omr, omc = oc.rectify_map(ch, 1.0 / ratio, axs, sz)
+    inb = (omr >= 1.001) & (omr <= sz[0] - 0.001) & (omc >= 1.001) & (omc <= sz[1] - 0.001)
+    assert not np.any(np.isnan(got[0][inb]))
+    # ramp values carry FP32 rounding of the blend (ulp(4096) = 4.9e-4): allow for it
+    assert np.max(np.abs(got[0][inb] - omr[inb])) <= TOL32_PX + 5e-4
+    assert np.max(np.abs(got[1][inb] - omc[inb])) <= TOL32_PX + 5e-4
+    # fill decisions differ only within 1e-3 px of the frame border
+    edge = ~inb & ~((omr < 0.999) | (omr > sz[0] + 0.001) | (omc < 0.999) | (omc > sz[1] + 0.001))
+    outside = ~inb & ~edge
+    assert np.all(np.isnan(got[0][outside]))
+    # u8 fast path: at most 1 LSB away from the FP64 result, and rarely
+    rng = np.random.default_rng(5)
+    f8 = rng.integers(0, 256, (1, sz[1], sz[0], 3), dtype=np.uint8)
+    # smooth image so that a 1e-3 px shift cannot move a value by more than 1 LSB
+    f8 = (np.add.outer(np.arange(sz[1]) // 7, np.arange(sz[0]) // 5) % 256).astype(np.uint8)[None, :, :, None].repeat(3, -1)
+    a = cc.warp(c, 0, _dev(f8), ratio, axs, coord="f32").cpu().numpy().astype(np.int16)
+    b = oc.rectify_u8c3(ch, 1.0 / ratio, axs, f8).astype(np.int16)
+    diff = np.abs(a - b)[0][inb]
+    assert diff.max() <= 1 and (diff > 0).mean() < 5e-3
+
+
+def test_rectify_batch_frames_independent(cc):
+    """Size-independent property at BASELINE config 2 size: every frame of a batch is
+    processed identically (equal inputs -> bitwise equal outputs), strided layouts work."""
+    sz = (1080, 1920)
+    ch, ip, ratio, axs = _rect_case(C2_INTR, sz, view=BENCH_VIEW)
+    c = _calib(cc, C2_INTR, [BENCH_VIEW])
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    one = torch.rand((1, sz[1], sz[0]), device="cuda", generator=g)
+    batch = one.repeat(8, 1, 1).contiguous()
+    out = cc.warp(c, 0, batch, ratio, axs)
+    assert all(torch.equal(torch.nan_to_num(out[0], nan=-1.0), torch.nan_to_num(out[i], nan=-1.0))
+               for i in range(1, 8))
+    ref = oc.rectify_f32c1(ch, 1.0 / ratio, axs, one.cpu().numpy(), fill=-1.0)
+    assert np.array_equal(torch.nan_to_num(out[3], nan=-1.0).cpu().numpy(), ref[0])
+    assert (ref[0] != -1.0).mean() > 0.99      # >= 99 % of output pixels sample in-bounds
+
+
+# ------------------------------------------------------------------ residual / Jacobian
+def _c5_case(nviews, seed=7):
+    rng = np.random.default_rng(seed)
+    n1, n2 = 20, 14
+    intr = C3_INTR
+    obj = np.array([[a, b, 0.0] for b in range(n2) for a in range(n1)], dtype=np.float64)
+    rv = rng.normal(0, 0.3, (nviews, 3))
+    tv = np.array([-10.0, -7.0, 40.0]) + rng.normal(0, 2.0, (nviews, 3))
+    views = [(rv[i], tv[i]) for i in range(nviews)]
+    img = np.empty((nviews, n1 * n2, 2))
+    for i in range(nviews):
+        r, q = oc.world2img(oc.chain(intr, rv[i], tv[i]), obj)
+        img[i, :, 0], img[i, :, 1] = r, q
+    img += rng.normal(0, 0.25, img.shape)
+    return intr, views, np.concatenate([rv, tv], axis=1), obj, img, (n1, n2)
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / (1.0 + np.abs(b)))
+
+
+def test_reproj_jtj_vs_oracle(cc):
+    intr, views, vt, obj, img, _ = _c5_case(257)
+    pv_o, sh_o, _ = oc.reproj_jtj(intr, 1.0, views, obj, img)
+    pv, sh = cc.reproj_jtj(intr, 1.0, _dev(vt), _dev(obj), _dev(img))
+    assert _relerr(pv.cpu().numpy(), pv_o) <= TOL64
+    assert _relerr(sh.cpu().numpy(), sh_o) <= TOL64
+    # bit-reproducible (fixed reduction order)
+    pv2, sh2 = cc.reproj_jtj(intr, 1.0, _dev(vt), _dev(obj), _dev(img))
+    assert torch.equal(pv, pv2) and torch.equal(sh, sh2)
+    # host entry point
+    pv_h, sh_h = cc.reproj_jtj(intr, 1.0, vt, obj, img)
+    assert np.array_equal(pv_h, pv.cpu().numpy()) and np.array_equal(sh_h, sh.cpu().numpy())
+    # aspect != 1 and checker_size != 1
+    intr2 = (intr[0] * 1.1,) + intr[1:5] + (2.5,)
+    pv_o, sh_o, _ = oc.reproj_jtj(intr2, 1.1, views[:5], obj * 2.5, img[:5])
+    pv, sh = cc.reproj_jtj(intr2, 1.1, vt[:5], obj * 2.5, img[:5])
+    assert _relerr(pv, pv_o) <= TOL64 and _relerr(sh, sh_o) <= TOL64
+
+
+def test_reproj_jtj_vs_cv2_golden(cc, example_fit):
+    """J'J assembled from cv2.projectPoints' own Jacobian (tests/golden/project_points.json)."""
+    g = load_golden("project_points.json")
+    obj, img = example_fit["obj_np"], example_fit["corners_np"]
+    vt = np.array([list(r) + list(t) for r, t in example_fit["view_list"]])
+    pv, sh = cc.reproj_jtj(example_fit["intr_tuple"], 1.0, vt, obj, img)
+    tot = 0.0
+    for vi, gg in enumerate(g["example"]):
+        J = np.asarray(gg["jac"]).reshape(-1, 10)
+        r = (np.asarray(gg["pix"]) - img[vi]).reshape(-1)
+        JtJ = J.T @ J
+        assert _relerr(pv[vi, :36].reshape(6, 6), JtJ[:6, :6]) < 1e-8
+        assert _relerr(pv[vi, 36:60].reshape(6, 4), JtJ[:6, 6:]) < 1e-8
+        assert _relerr(pv[vi, 60:66], J[:, :6].T @ r) < 1e-8
+        tot += r @ r
+    assert abs(sh[20] - tot) < 1e-8
+    n = img.shape[0] * img.shape[1]
+    assert abs(np.sqrt(sh[20] / n) - example_fit["cv2_rms"]) < 1e-6
+
+
+def test_reproj_zero_theta_and_empty(cc):
+    intr, views, vt, obj, img, _ = _c5_case(3)
+    vt[0, :3] = 0.0
+    views[0] = (np.zeros(3), views[0][1])
+    pv_o, sh_o, _ = oc.reproj_jtj(intr, 1.0, views, obj, img)
+    pv, sh = cc.reproj_jtj(intr, 1.0, vt, obj, img)
+    assert _relerr(pv, pv_o) <= TOL64 and _relerr(sh, sh_o) <= TOL64
+    pv, sh = cc.reproj_jtj(intr, 1.0, vt[:0], obj, img[:0])
+    assert pv.shape == (0, 66) and np.all(sh == 0.0)
+
+
+def test_calculate_errors_matches_reference_bounds(cc, example_fit):
+    """test/runtests.jl:73-77 through the CUDA path, and equality with the oracle."""
+    c = _calib(cc, example_fit["intr_tuple"], example_fit["view_list"], example_fit["files"])
+    rng = np.random.default_rng(1)
+    eps = cc.calculate_errors(c, example_fit["corners_np"], example_fit["obj_np"], 1.0, example_fit["sz"],
+                              example_fit["files"], example_fit["n_corners"], 100, rng=rng)
+    assert eps["n"] == 6
+    assert all(eps[k] < 1 for k in ("reprojection", "projection", "distance", "inverse"))
+    rng = np.random.default_rng(1)
+    sz = np.asarray(example_fit["sz"], dtype=np.float64)
+    samples = rng.random((6, 100, 2)) * (sz - 1) + 1
+    ref = oc.calculate_errors(example_fit["intr_tuple"], example_fit["view_list"], example_fit["obj_np"],
+                              example_fit["corners_np"], example_fit["n_corners"], samples)
+    for k, r in zip(("reprojection", "projection", "distance"), ref[:3]):
+        assert abs(eps[k] - r) <= 1e-9
+    assert eps["inverse"] < 1e-10 and ref[3] < 1e-10
+
+
+def test_save_load_round_trip(cc, tmp_path, example_fit):
+    """test/runtests.jl:88-98 (files preserved) -- plus the numbers, which the reference leaves unpinned."""
+    c = _calib(cc, example_fit["intr_tuple"], example_fit["view_list"], example_fit["files"])
+    f = tmp_path / "calibration.json"
+    cc.save(f, c)
+    c2 = cc.load(f)
+    assert c2.files == c.files and c2.intrinsic == c.intrinsic and c2.k == c.k
+    assert c2.extrinsics == c.extrinsics and c2.scale == c.scale
+    p = np.array([[10.0, 20.0], [300.0, 400.0]])
+    assert np.array_equal(c(p, 2), c2(p, 2))
