@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): rectified Mpix/s.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, N B200s
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port of the reference)
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU (N > 1)
+
+A step = one pass of full-frame rectification over one batch of synthetic frames:
+  workload c2 (default): 64 frames 1080x1920 single-channel fp32 (BASELINE configs[1])
+  workload c3:           16 frames 2160x3840 u8 RGB per step (ring slice of configs[2])
+`value`  : whole-job Mpix/s with the batch resident in HBM (CUDA events, max over ranks)
+`e2e`    : the same metric through the host entry point of the C ABI (pinned host buffers,
+           H2D + D2H inside the timed region)
+`roofline`: algorithmic bytes / kernel time against the measured HBM copy bandwidth
+`cpu_baseline`: the oracle port of the reference's path on this box's host cores (rank 0, N=1)
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_CORNERS = (20, 14)
+BENCH_VIEW = ((0.05, -0.04, 0.02), (-9.3, -6.4, 30.0))   # >= 99 % of output pixels in bounds
+WORKLOADS = {
+    # name: (sz1, sz2, frames per step, channels, bytes/px algorithmic, intr)
+    "c2": dict(sz=(1080, 1920), frames=64, u8=False, bytes_per_px=8,
+               intr=(1400.0, 1400.0, 540.0, 960.0, -0.12, 1.0), seed=1234,
+               name="64 x 1080x1920 fp32 gray frames, full-frame rectification (BASELINE configs[1])"),
+    "c3": dict(sz=(2160, 3840), frames=16, u8=True, bytes_per_px=6,
+               intr=(2800.0, 2800.0, 1080.0, 1920.0, -0.12, 1.0), seed=4321,
+               name="16 x 2160x3840 u8 RGB frames per step (ring slice of BASELINE configs[2])"),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(key):
+    """per-launch dram bytes from the committed ncu --set full capture, if any"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(key)
+        except Exception:
+            return None
+    return None
+
+
+def geometry(wl):
+    """ratio / axs of the rectified output, from the synthetic board seen by the bench view.
+    Pure host arithmetic on 280 corners (numpy): parameters, not the measured path."""
+    intr, (rv, tv) = wl["intr"], BENCH_VIEW
+    th = np.linalg.norm(rv)
+    n = np.asarray(rv) / th
+    K = np.array([[0, -n[2], n[1]], [n[2], 0, -n[0]], [-n[1], n[0], 0]])
+    R = np.cos(th) * np.eye(3) + (1 - np.cos(th)) * np.outer(n, n) + np.sin(th) * K
+    n1, n2 = N_CORNERS
+    a, b = np.meshgrid(np.arange(n1, dtype=np.float64), np.arange(n2, dtype=np.float64), indexing="ij")
+    P = np.stack([a.ravel(), b.ravel(), np.zeros(a.size)], 1) @ R.T + np.asarray(tv)
+    uv = P[:, :2] / P[:, 2:3]
+    uv = uv * (1 + intr[4] * np.sum(uv * uv, 1, keepdims=True))
+    rc = uv * np.array(intr[:2]) + np.array(intr[2:4])
+    return rc.reshape(n1, n2, 2)
+
+
+class ClockSampler:
+    """SM clock + throttle reasons via NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def pinned_array(cc, shape, dtype):
+    """numpy view of cudaHostAlloc'ed memory (cc_host_alloc)"""
+    from cameracalibrations_b200 import _lib
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _lib.check(_lib.lib.cc_host_alloc(C.byref(p), C.c_size_t(nbytes)))
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def cpu_port(wl, nframes, nthreads, ratio, axs, steps=1, warmup=0):
+    """The oracle restatement of the reference's warp on the host cores (checker code used
+    only as the reported CPU baseline)."""
+    from oracle import oracle_c as oc
+    oc.build()
+    sz = wl["sz"]
+    ch = oc.chain(wl["intr"], *BENCH_VIEW)
+    rng = np.random.default_rng(wl["seed"])
+    if wl["u8"]:
+        frames = rng.integers(0, 256, (nframes, sz[1], sz[0], 3), dtype=np.uint8)
+        run = lambda: oc.rectify_u8c3(ch, 1.0 / ratio, axs, frames, nthreads=nthreads)
+    else:
+        frames = rng.random((nframes, sz[1], sz[0]), dtype=np.float32)
+        run = lambda: oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=np.nan, nthreads=nthreads)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return nframes * sz[0] * sz[1] / dt / 1e6, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--coord", default="f64", choices=["f64", "f32"],
+                    help="coordinate arithmetic of the map (f64 = the reference's precision)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "direct", "tma"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    sz = wl["sz"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = len(os.sched_getaffinity(0))
+
+    ip = geometry(wl)
+    metric, unit = "rectified_mpix_per_s", "Mpix/s"
+    config = {"workload": wl["name"], "frame": f"{sz[0]}x{sz[1]}", "frames_per_step_per_gpu": wl["frames"],
+              "pixel": "u8x3" if wl["u8"] else "f32x1", "view": BENCH_VIEW, "intr": wl["intr"],
+              "coord": args.coord, "parallelism": f"frame-sharded x{args.gpus} (no data-path collective)",
+              "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)"}
+
+    # ------------------------------------------------------------------ CPU arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle_c as oc
+        oc.build()
+        ip_ratio = oc.get_ratio(ip, wl["intr"][5])
+        axs = oc.get_axes(ip_ratio, wl["intr"][5], N_CORNERS, sz)
+        # bounded sample per step: sized from one timed frame so the run ends within minutes
+        _, per_frame = cpu_port(wl, 2, ncores, ip_ratio, axs)
+        per_frame /= 2
+        budget = 120.0 / (args.steps + args.warmup)
+        nfr = max(1, min(wl["frames"], int(budget / max(per_frame, 1e-9))))
+        v, dt = cpu_port(wl, nfr, ncores, ip_ratio, axs, steps=args.steps, warmup=args.warmup)
+        sample = f"{nfr} of {wl['frames']} frames per step, {args.steps} steps, {ncores} OpenMP threads"
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference's Julia path (Julia is not "
+                                     "installed on this image); faster than the Julia code would be"},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import cameracalibrations_b200 as cc
+    from cameracalibrations_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = cc.context(local_rank)
+    c = cc.Calibration(wl["intr"][:4], [BENCH_VIEW], 1.0 / wl["intr"][5], wl["intr"][4], ["extrinsic.png"])
+    ratio = cc.get_ratio(ip, wl["intr"][5])
+    axs = cc.get_axes(ratio, wl["intr"][5], N_CORNERS, sz)
+    nfr = wl["frames"]
+    npx = nfr * sz[0] * sz[1]
+
+    g = torch.Generator(device=dev).manual_seed(wl["seed"] + rank)
+    if wl["u8"]:
+        src = torch.randint(0, 256, (nfr, sz[1], sz[0], 3), dtype=torch.uint8, device=dev, generator=g)
+    else:
+        src = torch.rand((nfr, sz[1], sz[0]), dtype=torch.float32, device=dev, generator=g)
+    dst = torch.empty_like(src)
+    step = lambda: cc.warp(c, 0, src, ratio, axs, coord=args.coord, gather=args.gather, out=dst)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kern_ms = statistics.mean(per_step_ms)          # one kernel launch per step
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    value = world * npx * args.steps / (total_ms * 1e-3) / 1e6
+
+    # in-bounds fraction of the output (what share of the counted source bytes is really read)
+    if wl["u8"]:
+        inb = float((cc.warp(c, 0, torch.full_like(src[:1], 255), ratio, axs, coord=args.coord)[0, :, :, 0] == 255)
+                    .float().mean().item())
+    else:
+        inb = float((~torch.isnan(dst[0])).float().mean().item())
+    config["in_bounds_fraction"] = round(inb, 4)
+
+    peak, peak_src = measured_peak()
+    achieved = wl["bytes_per_px"] * npx / (kern_ms * 1e-3) / 1e9
+    kname = ("rectify_u8c3" if wl["u8"] else "rectify_f32c1") + "_" + args.coord
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(f"{args.workload}_{args.coord}"), "peak_source": peak_src,
+                "kernel": kname, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": wl["bytes_per_px"] * npx}
+
+    # ---- e2e: host entry point of the C ABI, pinned host buffers, copies in the timed region
+    px_bytes = 3 if wl["u8"] else 4
+    shape = tuple(src.shape)
+    h_src, p1 = pinned_array(cc, shape, np.uint8 if wl["u8"] else np.float32)
+    h_dst, p2 = pinned_array(cc, shape, np.uint8 if wl["u8"] else np.float32)
+    h_src[...] = src.cpu().numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        cc.warp(c, 0, h_src, ratio, axs, coord=args.coord, gather=args.gather, out=h_dst)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        cc.warp(c, 0, h_src, ratio, axs, coord=args.coord, gather=args.gather, out=h_dst)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * npx * e2e_steps / float(te.item()) / 1e6
+    same = bool(np.array_equal(np.nan_to_num(h_dst[0], nan=-1.0),
+                               np.nan_to_num(dst[0].cpu().numpy(), nan=-1.0)))
+    e2e = {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": npx * px_bytes,
+           "d2h_bytes_per_step": npx * px_bytes, "steps": e2e_steps,
+           "api": "cc_rectify_%s_host via cameracalibrations_b200.warp(numpy)" % ("u8c3" if wl["u8"] else "f32c1"),
+           "matches_device_path": same}
+    _lib.lib.cc_host_free(p1)
+    _lib.lib.cc_host_free(p2)
+    del h_src, h_dst
+
+    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": args.coord, "data": "synthetic", "config": config,
+           "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        out["extras"] = extras(cc, torch, dev, c, args)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nthreads = ncores
+        from oracle import oracle_c as oc
+        oc.build()
+        sample_frames = 16 if not wl["u8"] else 4
+        v, dt = cpu_port(wl, sample_frames, nthreads, ratio, axs, steps=2, warmup=1)
+        out["cpu_baseline"] = {"value": v, "unit": unit, "cores": nthreads, "kind": "port",
+                               "sample": f"{sample_frames} of {nfr} frames x 2 timed passes ({dt:.2f} s each), "
+                                         f"{nthreads} OpenMP threads"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time_ms(torch, fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def extras(cc, torch, dev, c2cal, args):
+    """Secondary workloads of BASELINE.json (device-resident, CUDA events): the other
+    coordinate mode, 4K u8 RGB, 100 M point maps, residual + J'J."""
+    peak, _ = measured_peak()
+    ex = {}
+    # the other variants of the rectification kernels
+    for wname in ("c2", "c3"):
+        wl = WORKLOADS[wname]
+        sz, nfr = wl["sz"], wl["frames"]
+        cal = cc.Calibration(wl["intr"][:4], [BENCH_VIEW], 1.0, wl["intr"][4], ["extrinsic.png"])
+        ratio = cc.get_ratio(geometry(wl), 1.0)
+        axs = cc.get_axes(ratio, 1.0, N_CORNERS, sz)
+        if wl["u8"]:
+            src = torch.randint(0, 256, (nfr, sz[1], sz[0], 3), dtype=torch.uint8, device=dev)
+        else:
+            src = torch.rand((nfr, sz[1], sz[0]), dtype=torch.float32, device=dev)
+        dst = torch.empty_like(src)
+        for coord in ("f64", "f32"):
+            if wname == args.workload and coord == args.coord:
+                continue
+            ms = _time_ms(torch, lambda: cc.warp(cal, 0, src, ratio, axs, coord=coord, gather=args.gather, out=dst), 20)
+            npx = nfr * sz[0] * sz[1]
+            gbs = wl["bytes_per_px"] * npx / (ms * 1e-3) / 1e9
+            ex[f"rectify_{wname}_{coord}"] = {"mpix_per_s": npx / (ms * 1e-3) / 1e6, "ms": ms, "gb_per_s": gbs,
+                                              "hbm_frac": gbs / peak}
+        del src, dst
+    # C4: 100 M random RowCol -> world, FP64 and FP32
+    wl = WORKLOADS["c3"]
+    cal = cc.Calibration(wl["intr"][:4], [BENCH_VIEW], 1.0, wl["intr"][4], ["extrinsic.png"])
+    n = 100_000_000
+    for dt, name, bpp in ((torch.float64, "f64", 40), (torch.float32, "f32", 20)):
+        g = torch.Generator(device=dev).manual_seed(99)
+        row = torch.rand(n, dtype=dt, device=dev, generator=g) * 2160
+        col = torch.rand(n, dtype=dt, device=dev, generator=g) * 3840
+        ms = _time_ms(torch, lambda: cal.img2world(row, col, 0), 10)
+        x, y, z = cal.img2world(row, col, 0)
+        ex[f"img2world_{name}_100M"] = {"gpt_per_s": n / (ms * 1e-3) / 1e9, "ms": ms,
+                                        "gb_per_s": bpp * n / (ms * 1e-3) / 1e9,
+                                        "hbm_frac": bpp * n / (ms * 1e-3) / 1e9 / peak}
+        ms = _time_ms(torch, lambda: cal.world2img(x, y, z, 0), 10)
+        ex[f"world2img_{name}_100M"] = {"gpt_per_s": n / (ms * 1e-3) / 1e9, "ms": ms,
+                                        "gb_per_s": bpp * n / (ms * 1e-3) / 1e9,
+                                        "hbm_frac": bpp * n / (ms * 1e-3) / 1e9 / peak}
+        del row, col, x, y, z
+    # C5: residual + J'J over 10k views x 280 corners
+    rng = np.random.default_rng(7)
+    nv, nc = 10_000, 280
+    views = np.concatenate([rng.normal(0, 0.3, (nv, 3)), np.array([-10.0, -7.0, 40.0]) + rng.normal(0, 2.0, (nv, 3))], 1)
+    obj = np.array([[a, b, 0.0] for b in range(14) for a in range(20)], dtype=np.float64)
+    tv = torch.from_numpy(views).to(dev)
+    to = torch.from_numpy(obj).to(dev)
+    ti = torch.rand((nv, nc, 2), dtype=torch.float64, device=dev) * 2000
+    ms = _time_ms(torch, lambda: cc.reproj_jtj(wl["intr"], 1.0, tv, to, ti), 20)
+    ex["reproj_jtj_10k_views"] = {"views_per_s": nv / (ms * 1e-3), "ms": ms,
+                                  "gb_per_s": 4936 * nv / (ms * 1e-3) / 1e9}
+    return ex
+
+
+if __name__ == "__main__":
+    main()
