@@ -22,54 +22,65 @@ constexpr int kRectThreads = 32 * kTile2;
 
 // ---------------------------------------------------------------------------------
 // fp32 single channel, direct gather through L1/L2.
-// Lane l of a warp owns pixels a = tile + 32*e + l (e = 0..3): consecutive lanes sample
-// consecutive source texels, so one gather request touches ~5 sectors (the first layout,
-// 4 consecutive pixels per lane, touched 16.7: profiles/r1_rectify_direct_v1.md) and every
-// store instruction writes one full 128-byte line.
+// One warp per output line (fixed I2): everything that depends on I2 only is computed
+// once per line; the warp then walks the line in batches of 4 x 32 pixels.  Lane l owns
+// pixels a = 128*batch + 32*e + l (e = 0..3): consecutive lanes sample consecutive source
+// texels, so one gather request touches ~5 sectors (the first layout, 4 consecutive pixels
+// per lane, touched 16.7: profiles/r1_rectify.md) and every store instruction writes one
+// full 128-byte line.  Addresses are 32-bit element offsets from a per-frame base.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ const float* elem_ptr(const float* base, unsigned idx) {
+    const float* q;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q) : "r"(idx), "l"(base));
+    return q;
+}
+
 __global__ void __launch_bounds__(kRectThreads)
 rectify_f32c1_exact(const RectExact p, const RectGeom g, const float* __restrict__ src,
                     float* __restrict__ dst, float fill) {
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y * kTile2 + warp;
+    const int b = blockIdx.x * kTile2 + warp;
     if (b >= g.sz2) return;
-    const int a_base = blockIdx.x * kTile1 + lane_id;
-    const float* s = src + (long long)blockIdx.z * g.frame_stride;
-    float* o = dst + (long long)blockIdx.z * g.frame_stride + (long long)b * g.pitch;
+    const float* s = src + (long long)blockIdx.y * g.frame_stride;
+    float* o = dst + (long long)blockIdx.y * g.frame_stride + (long long)b * g.pitch;
     const ColTermD ct = rect_col_term(p, g.axs1 + b);
     const unsigned pitch = (unsigned)g.pitch;
 
-    unsigned idx[kChunks];
-    bool ok[kChunks];
-    double d1[kChunks], d2[kChunks];
+    for (int a0 = lane_id; a0 < g.sz1; a0 += kTile1) {
+        unsigned idx[kChunks];
+        bool ok[kChunks];
+        double d1[kChunks], d2[kChunks];
 #pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        double row, col;
-        rect_coord(p, ct, g.axs0 + a_base + 32 * e, row, col);
-        int i1, i2;
-        const bool v1 = lin_pos(row, g.sz1, i1, d1[e]);
-        const bool v2 = lin_pos(col, g.sz2, i2, d2[e]);
-        ok[e] = v1 & v2;
-        idx[e] = (unsigned)i2 * pitch + (unsigned)i1;
-    }
-    float a00[kChunks], a10[kChunks], a01[kChunks], a11[kChunks];
-#pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        if (ok[e]) {
-            const float* q = s + idx[e];
-            a00[e] = __ldg(q);
-            a10[e] = __ldg(q + 1);
-            a01[e] = __ldg(q + pitch);
-            a11[e] = __ldg(q + pitch + 1);
+        for (int e = 0; e < kChunks; ++e) {
+            double row, col;
+            rect_coord(p, ct, g.axs0 + a0 + 32 * e, row, col);
+            int i1, i2;
+            const bool v1 = lin_pos(row, g.sz1, i1, d1[e]);
+            const bool v2 = lin_pos(col, g.sz2, i2, d2[e]);
+            ok[e] = v1 & v2;
+            idx[e] = (unsigned)i2 * pitch + (unsigned)i1;
         }
-    }
+        float a00[kChunks], a10[kChunks], a01[kChunks], a11[kChunks];
 #pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        const int a = a_base + 32 * e;
-        const float v = ok[e] ? (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
-                                              (double)a11[e], d1[e], d2[e])
-                              : fill;
-        if (a < g.sz1) __stcs(o + a, v);
+        for (int e = 0; e < kChunks; ++e) {
+            const float* q = elem_ptr(s, idx[e]);
+            const float* q2 = elem_ptr(s, idx[e] + pitch);
+            if (ok[e]) {
+                a00[e] = __ldg(q);
+                a10[e] = __ldg(q + 1);
+                a01[e] = __ldg(q2);
+                a11[e] = __ldg(q2 + 1);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kChunks; ++e) {
+            const int a = a0 + 32 * e;
+            float v = fill;
+            if (ok[e])
+                v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
+                                  d1[e], d2[e]);
+            if (a < g.sz1) __stcs(o + a, v);
+        }
     }
 }
 
@@ -77,44 +88,47 @@ __global__ void __launch_bounds__(kRectThreads)
 rectify_f32c1_fast(const RectFast p, const RectGeom g, const float* __restrict__ src,
                    float* __restrict__ dst, float fill) {
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y * kTile2 + warp;
+    const int b = blockIdx.x * kTile2 + warp;
     if (b >= g.sz2) return;
-    const int a_base = blockIdx.x * kTile1 + lane_id;
-    const float* s = src + (long long)blockIdx.z * g.frame_stride;
-    float* o = dst + (long long)blockIdx.z * g.frame_stride + (long long)b * g.pitch;
+    const float* s = src + (long long)blockIdx.y * g.frame_stride;
+    float* o = dst + (long long)blockIdx.y * g.frame_stride + (long long)b * g.pitch;
     const ColTermF ct = rect_col_term(p, g.axs1 + b);
     const unsigned pitch = (unsigned)g.pitch;
-    const float i1f0 = (float)(g.axs0 + a_base) - p.c1;
+    float i1f = (float)(g.axs0 + lane_id) - p.c1;
 
-    unsigned idx[kChunks];
-    bool ok[kChunks];
-    float d1[kChunks], d2[kChunks];
+    for (int a0 = lane_id; a0 < g.sz1; a0 += kTile1, i1f += (float)kTile1) {
+        unsigned idx[kChunks];
+        bool ok[kChunks];
+        float d1[kChunks], d2[kChunks];
 #pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        float row, col;
-        rect_coord(p, ct, i1f0 + 32.0f * e, row, col);
-        int i1, i2;
-        const bool v1 = lin_pos_fast(row, g.sz1, i1, d1[e]);
-        const bool v2 = lin_pos_fast(col, g.sz2, i2, d2[e]);
-        ok[e] = v1 & v2;
-        idx[e] = (unsigned)i2 * pitch + (unsigned)i1;
-    }
-    float a00[kChunks], a10[kChunks], a01[kChunks], a11[kChunks];
-#pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        if (ok[e]) {
-            const float* q = s + idx[e];
-            a00[e] = __ldg(q);
-            a10[e] = __ldg(q + 1);
-            a01[e] = __ldg(q + pitch);
-            a11[e] = __ldg(q + pitch + 1);
+        for (int e = 0; e < kChunks; ++e) {
+            float row, col;
+            rect_coord(p, ct, i1f + 32.0f * e, row, col);
+            int i1, i2;
+            const bool v1 = lin_pos_fast(row, g.sz1, i1, d1[e]);
+            const bool v2 = lin_pos_fast(col, g.sz2, i2, d2[e]);
+            ok[e] = v1 & v2;
+            idx[e] = (unsigned)i2 * pitch + (unsigned)i1;
         }
-    }
+        float a00[kChunks], a10[kChunks], a01[kChunks], a11[kChunks];
 #pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        const int a = a_base + 32 * e;
-        const float v = ok[e] ? bilerp_fast(a00[e], a10[e], a01[e], a11[e], d1[e], d2[e]) : fill;
-        if (a < g.sz1) __stcs(o + a, v);
+        for (int e = 0; e < kChunks; ++e) {
+            const float* q = elem_ptr(s, idx[e]);
+            const float* q2 = elem_ptr(s, idx[e] + pitch);
+            if (ok[e]) {
+                a00[e] = __ldg(q);
+                a10[e] = __ldg(q + 1);
+                a01[e] = __ldg(q2);
+                a11[e] = __ldg(q2 + 1);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kChunks; ++e) {
+            const int a = a0 + 32 * e;
+            float v = fill;
+            if (ok[e]) v = bilerp_fast(a00[e], a10[e], a01[e], a11[e], d1[e], d2[e]);
+            if (a < g.sz1) __stcs(o + a, v);
+        }
     }
 }
 
@@ -303,7 +317,7 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
                          cudaStream_t st) {
     if (nframes == 0) return CC_OK;
     CC_REQUIRE((flags & CC_GATHER_TMA) == 0, "TMA gather not available for this layout");
-    const dim3 grid = rect_grid(sz1, sz2, nframes);
+    const dim3 grid((sz2 + kTile2 - 1) / kTile2, nframes);
     const RectGeom g = make_geom(axs_min, sz1, sz2, pitch, frame_stride, nframes);
     if (flags & CC_COORD_F32)
         rectify_f32c1_fast<<<grid, kRectThreads, 0, st>>>(make_fast(chd, ratio, g), g, src, dst, fill);
