@@ -15,9 +15,9 @@ namespace cc {
 __device__ __forceinline__ void world2img(const ChainD& ch, double x, double y, double z,
                                           double& row, double& col) {
     const double q1 = x * ch.inv_cs, q2 = y * ch.inv_cs, q3 = z * ch.inv_cs;
-    const double P1 = fma(ch.R[0], q1, fma(ch.R[1], q2, fma(ch.R[2], q3, ch.t[0])));
-    const double P2 = fma(ch.R[3], q1, fma(ch.R[4], q2, fma(ch.R[5], q3, ch.t[1])));
-    const double P3 = fma(ch.R[6], q1, fma(ch.R[7], q2, fma(ch.R[8], q3, ch.t[2])));
+    const double P1 = fma(ch.R[1], q2, fma(ch.R[0], q1, fma(ch.R[2], q3, ch.t[0])));
+    const double P2 = fma(ch.R[4], q2, fma(ch.R[3], q1, fma(ch.R[5], q3, ch.t[1])));
+    const double P3 = fma(ch.R[7], q2, fma(ch.R[6], q1, fma(ch.R[8], q3, ch.t[2])));
     const double s = 1.0 / P3;                        // PerspectiveMap: scale = 1/v[3]
     double u = P1 * s, v = P2 * s;
     if (ch.k != 0.0) {                                // lens_distortion, src/meta.jl:39-44
@@ -33,9 +33,9 @@ __device__ __forceinline__ void world2img(const ChainD& ch, double x, double y, 
 __device__ __forceinline__ void world2img(const ChainF& ch, float x, float y, float z,
                                           float& row, float& col) {
     const float q1 = x * ch.inv_cs, q2 = y * ch.inv_cs, q3 = z * ch.inv_cs;
-    const float P1 = fmaf(ch.R[0], q1, fmaf(ch.R[1], q2, fmaf(ch.R[2], q3, ch.t[0])));
-    const float P2 = fmaf(ch.R[3], q1, fmaf(ch.R[4], q2, fmaf(ch.R[5], q3, ch.t[1])));
-    const float P3 = fmaf(ch.R[6], q1, fmaf(ch.R[7], q2, fmaf(ch.R[8], q3, ch.t[2])));
+    const float P1 = fmaf(ch.R[1], q2, fmaf(ch.R[0], q1, fmaf(ch.R[2], q3, ch.t[0])));
+    const float P2 = fmaf(ch.R[4], q2, fmaf(ch.R[3], q1, fmaf(ch.R[5], q3, ch.t[1])));
+    const float P3 = fmaf(ch.R[7], q2, fmaf(ch.R[6], q1, fmaf(ch.R[8], q3, ch.t[2])));
     const float s = __frcp_rn(P3);
     float u = P1 * s, v = P2 * s;
     if (ch.k != 0.0f) {

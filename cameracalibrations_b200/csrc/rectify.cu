@@ -1,152 +1,306 @@
 // rectify.cu -- full-frame rectification (backward warp + bilinear gather).
 //
 // Replaces warp(img, tform, axs) of src/plot_calibration.jl:40 (tform/axs from
-// image_transformations :15-22 and get_axes :1-6) for batches of frames that share
-// one view.  The map is computed in-kernel and never stored: algorithmic traffic is
-// one read + one write of every pixel (8 B/px fp32 gray, 6 B/px u8 RGB).
+// image_transformations :15-22 and get_axes :1-6) for batches of frames that share one
+// view.  The map is computed in-kernel and never stored: algorithmic traffic is one read
+// and one write of every pixel (8 B/px fp32 gray, 6 B/px u8 RGB).
 //
-// Thread layout: the first RowCol axis is contiguous in memory, so a warp covers
-// 128 consecutive first-axis pixels (4 per lane -> one 128-bit store per lane for
-// fp32), a CTA of 8 warps covers 8 consecutive second-axis lines: a 128 x 8 output
-// tile whose source footprint is a compact patch that stays in L1/L2.
+// Work decomposition.  The first RowCol axis is contiguous in memory.  A CTA owns a STRIP
+// of 32 consecutive first-axis pixels (lane = pixel, so every store instruction writes one
+// full 128-byte line and consecutive lanes sample consecutive source texels) and marches
+// down the second axis in 32 x 32 TILES; warp w owns lines 4w..4w+3 of each tile.  A thread
+// therefore keeps I1 fixed for its whole life: the I1-dependent half of the extrinsic is
+// hoisted out of the pixel loop.  Square tiles keep the source footprint of a tile compact
+// for any in-plane rotation (35 x 35 texels for the bench view, profiles/r1_rectify.md).
+//
+// Gather.  Two variants of every kernel:
+//  * TMA-staged: a ninth warp is the producer.  For each tile it evaluates the map at the
+//    four tile corners, takes the bounding box of the source footprint and issues ONE
+//    cp.async.bulk.tensor (3-D tensor map over (first axis, second axis, frame)) into a
+//    ring of shared-memory stages guarded by full/empty mbarriers; out-of-frame parts of
+//    the box are zero-filled by the TMA unit.  The eight consumer warps gather their four
+//    taps with LDS from the staged box.  A pixel whose taps are not inside the box (border
+//    tiles, or a footprint larger than the box) falls back to direct global loads, so the
+//    box estimate affects speed only, never results.
+//  * Direct: the same kernel without the producer; taps come through L1/L2 (__ldg).
+#include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <mutex>
 
 #include "rectify_device.cuh"
+#include "tma.cuh"
 
 namespace cc {
 
-constexpr int kChunks = 4;              // 32-pixel chunks per warp along the contiguous axis
-constexpr int kTile1 = 32 * kChunks;    // 128
-constexpr int kTile2 = 8;               // warps per CTA = second-axis lines per tile
-constexpr int kRectThreads = 32 * kTile2;
+constexpr int kT = 32;                 // tile edge
+constexpr int kWarps = 4;              // consumer warps per CTA
+constexpr int kLines = kT / kWarps;    // lines per warp per tile = pixels per thread per tile
+constexpr int kBatch = 4;              // lines whose taps are in flight together
+constexpr int kMaxStages = 4;
+constexpr int kConsumerThreads = 32 * kWarps;
 
-// ---------------------------------------------------------------------------------
-// fp32 single channel, direct gather through L1/L2.
-// One warp per output line (fixed I2): everything that depends on I2 only is computed
-// once per line; the warp then walks the line in batches of 4 x 32 pixels.  Lane l owns
-// pixels a = 128*batch + 32*e + l (e = 0..3): consecutive lanes sample consecutive source
-// texels, so one gather request touches ~5 sectors (the first layout, 4 consecutive pixels
-// per lane, touched 16.7: profiles/r1_rectify.md) and every store instruction writes one
-// full 128-byte line.  Addresses are 32-bit element offsets from a per-frame base.
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ const float* elem_ptr(const float* base, unsigned idx) {
-    const float* q;
-    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q) : "r"(idx), "l"(base));
-    return q;
+struct TileCfg {
+    int box1, box2;        // staged box, in pixels (box1 along the contiguous axis)
+    int stages;
+    int tiles_per_seg;     // tiles one CTA walks
+    int ntiles2;           // tiles along the second axis
+    int box_bytes;         // bytes one TMA load delivers = stage stride (multiple of 128)
+};
+
+// per-stage header written by the producer warp
+struct __align__(16) StageHdr {
+    int x0, y0;            // box origin (0-based texel indices; may be negative)
+    int K1, R1, K2, R2;    // fused index / range constants (see consumer)
+    int base_off;          // pixel offset of (lo1, lo2) inside the box
+    int pad;
+    double q2[kT];         // exact path: second-axis world term of every line of the tile
+};
+
+struct SmemCtl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    StageHdr hdr[kMaxStages];
+};
+
+// --------------------------------------------------------------------------------------
+// producer: box origin from the four tile corners (FP32 map, even for the exact kernels --
+// it only positions the box), header, TMA issue.  PXB = 1 (f32c1 elements) or 3 (u8c3 bytes).
+// --------------------------------------------------------------------------------------
+template <bool EXACT, int PXB>
+__device__ __forceinline__ void producer_tile(const CUtensorMap* tmap, const RectFast& pf,
+                                              const RectExact& pe, const RectGeom& g,
+                                              const TileCfg& cfg, SmemCtl* ctl, uint8_t* stage,
+                                              int s, int a_lo, int tile, int frame, int lane_id) {
+    const int b_lo = tile * kT;
+    const int a_hi = min(a_lo + kT - 1, g.sz1 - 1), b_hi = min(b_lo + kT - 1, g.sz2 - 1);
+    const int ca = (lane_id & 1) ? a_hi : a_lo, cb = (lane_id & 2) ? b_hi : b_lo;   // lanes 0..3: corners
+    const RowTermF rt = rect_row_term(pf, g.axs0 + ca);
+    float row, col;
+    rect_coord(pf, rt, (float)(g.axs1 + cb) - pf.c2, row, col);
+    // clamp so that NaN / far-away footprints still give a legal (fully out-of-frame) box
+    row = fminf(fmaxf(row, -4.0f), (float)g.sz1 + 4.0f);
+    col = fminf(fmaxf(col, -4.0f), (float)g.sz2 + 4.0f);
+    int r0 = (row == row) ? (int)floorf(row) : -4;
+    int c0 = (col == col) ? (int)floorf(col) : -4;
+    r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, 1));
+    r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, 2));
+    c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, 1));
+    c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    // first tap index is floor - 1 (0-based); one texel of slack for the FP32 estimate.
+    // The first-axis origin is rounded down so that the byte address stays 16-byte aligned.
+    int x0 = __shfl_sync(0xffffffffu, r0, 0) - 2;
+    const int y0 = __shfl_sync(0xffffffffu, c0, 0) - 2;
+    constexpr int kAlign = (PXB == 1) ? 4 : 16;
+    x0 = (x0 >= 0) ? (x0 / kAlign) * kAlign : -(((-x0) + kAlign - 1) / kAlign) * kAlign;
+    StageHdr* h = &ctl->hdr[s];
+    if (EXACT) h->q2[lane_id] = rect_q2(pe, g.axs1 + b_lo + lane_id);
+    if (lane_id == 0) {
+        // valid local range of the first tap: inside the box (both taps) and inside the frame
+        const int lo1 = max(0, -x0), hi1 = min(cfg.box1 - 2, g.sz1 - 2 - x0);
+        const int lo2 = max(0, -y0), hi2 = min(cfg.box2 - 2, g.sz2 - 2 - y0);
+        h->x0 = x0; h->y0 = y0;
+        h->K1 = (EXACT ? 1 : kMagicBits + 1) + x0 + lo1;
+        h->K2 = (EXACT ? 1 : kMagicBits + 1) + y0 + lo2;
+        h->R1 = max(0, hi1 - lo1 + 1);
+        h->R2 = max(0, hi2 - lo2 + 1);
+        h->base_off = lo2 * cfg.box1 + lo1;
+    }
+    __syncwarp();
+    if (lane_id == 0) {
+        mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)cfg.box_bytes);
+        tma_load_3d(stage, tmap, &ctl->full[s], x0 * PXB, y0, frame);
+    }
 }
 
-__global__ void __launch_bounds__(kRectThreads)
-rectify_f32c1_exact(const RectExact p, const RectGeom g, const float* __restrict__ src,
-                    float* __restrict__ dst, float fill) {
-    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * kTile2 + warp;
-    if (b >= g.sz2) return;
-    const float* s = src + (long long)blockIdx.y * g.frame_stride;
-    float* o = dst + (long long)blockIdx.y * g.frame_stride + (long long)b * g.pitch;
-    const ColTermD ct = rect_col_term(p, g.axs1 + b);
-    const unsigned pitch = (unsigned)g.pitch;
+__device__ __forceinline__ void pipeline_init(SmemCtl* ctl, int stages, bool tma) {
+    if (tma && threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], kWarps);
+        }
+        mbar_fence_init();
+    }
+    if (tma) __syncthreads();
+}
 
-    for (int a0 = lane_id; a0 < g.sz1; a0 += kTile1) {
-        unsigned idx[kChunks];
-        bool ok[kChunks];
-        double d1[kChunks], d2[kChunks];
-#pragma unroll
-        for (int e = 0; e < kChunks; ++e) {
-            double row, col;
-            rect_coord(p, ct, g.axs0 + a0 + 32 * e, row, col);
-            int i1, i2;
-            const bool v1 = lin_pos(row, g.sz1, i1, d1[e]);
-            const bool v2 = lin_pos(col, g.sz2, i2, d2[e]);
-            ok[e] = v1 & v2;
-            idx[e] = (unsigned)i2 * pitch + (unsigned)i1;
+// --------------------------------------------------------------------------------------
+// fp32 single channel
+// --------------------------------------------------------------------------------------
+// generic per-pixel path: every check, direct global taps.  Used by the direct variant and,
+// in the staged variant, by the (border) warps whose taps are not all inside the staged box.
+template <bool EXACT>
+__device__ __forceinline__ float sample_direct_f32(const RectExact& pe, const RectFast& pf,
+                                                   const RowTermD& rtd, const RowTermF& rtf,
+                                                   const RectGeom& g, const float* __restrict__ sframe,
+                                                   unsigned pitch, int b, float fill) {
+    if (EXACT) {
+        double row, col, d1, d2;
+        int i1, i2;
+        rect_coord(pe, rtd, rect_q2(pe, g.axs1 + b), row, col);
+        if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) return fill;
+        lin_floor(row, i1, d1);
+        lin_floor(col, i2, d2);
+        lin_fix_edge(g.sz1, i1, d1);
+        lin_fix_edge(g.sz2, i2, d2);
+        const float* q = sframe + ((unsigned)(i2 - 1) * pitch + (unsigned)(i1 - 1));
+        return (float)bilerp((double)__ldg(q), (double)__ldg(q + 1), (double)__ldg(q + pitch),
+                             (double)__ldg(q + pitch + 1), d1, d2);
+    } else {
+        float row, col, d1, d2;
+        int t1, t2;
+        rect_coord(pf, rtf, (float)(g.axs1 + b) - pf.c2, row, col);
+        lin_floor_fast(row, t1, d1);
+        lin_floor_fast(col, t2, d2);
+        const int g1 = t1 - (kMagicBits + 1), g2 = t2 - (kMagicBits + 1);
+        if (!(((unsigned)g1 <= (unsigned)(g.sz1 - 2)) & ((unsigned)g2 <= (unsigned)(g.sz2 - 2)))) return fill;
+        const float* q = sframe + ((unsigned)g2 * pitch + (unsigned)g1);
+        return bilerp_fast(__ldg(q), __ldg(q + 1), __ldg(q + pitch), __ldg(q + pitch + 1), d1, d2);
+    }
+}
+
+template <bool EXACT, bool TMA>
+__global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads)
+rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
+                     const RectGeom g, const TileCfg cfg, const float* __restrict__ src,
+                     float* __restrict__ dst, float fill) {
+    extern __shared__ __align__(128) uint8_t stage_mem[];
+    __shared__ SmemCtl ctl;
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a_lo = blockIdx.x * kT;
+    const int frame = blockIdx.z;
+    const int t_begin = blockIdx.y * cfg.tiles_per_seg;
+    const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
+    pipeline_init(&ctl, cfg.stages, TMA);
+
+    if (TMA && warp == kWarps) {                       // ---- producer warp
+        if (lane_id == 0) tma_prefetch_desc(&tmap);
+        int s = 0;
+        uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
+        for (int tile = t_begin; tile < t_end; ++tile) {
+            mbar_wait(&ctl.empty[s], phase);
+            producer_tile<EXACT, 1>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
+                                    s, a_lo, tile, frame, lane_id);
+            if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
-        float a00[kChunks], a10[kChunks], a01[kChunks], a11[kChunks];
+        return;
+    }
+
+    // ---- consumer warps
+    const int a = a_lo + lane_id;
+    const bool a_in = a < g.sz1;
+    const float* sframe = src + (long long)frame * g.frame_stride;
+    const unsigned pitch = (unsigned)g.pitch;
+    const int box1 = cfg.box1;
+    RowTermD rtd;
+    RowTermF rtf;
+    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+    const int line0 = t_begin * kT + warp * kLines;
+    float* optr = dst + (long long)frame * g.frame_stride + (long long)line0 * g.pitch + a;
+    float i2f = (float)(g.axs1 + line0) - pf.c2;       // fast path: second-axis index, advanced per line
+    const long long tile_step = (long long)(kT - kLines) * g.pitch;
+
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const int b0 = tile * kT + warp * kLines;
+        const bool full_lines = b0 + kLines <= g.sz2;
+        int K1 = 0, R1 = 0, K2 = 0, R2 = 0;
+        const float* box = nullptr;
+        const StageHdr* h = &ctl.hdr[s];
+        if (TMA) {
+            mbar_wait(&ctl.full[s], phase);
+            K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
+            box = reinterpret_cast<const float*>(stage_mem + (size_t)s * cfg.box_bytes) + h->base_off;
+        }
 #pragma unroll
-        for (int e = 0; e < kChunks; ++e) {
-            const float* q = elem_ptr(s, idx[e]);
-            const float* q2 = elem_ptr(s, idx[e] + pitch);
-            if (ok[e]) {
-                a00[e] = __ldg(q);
-                a10[e] = __ldg(q + 1);
-                a01[e] = __ldg(q2);
-                a11[e] = __ldg(q2 + 1);
+        for (int batch = 0; batch < kLines / kBatch; ++batch) {
+            const int bb = b0 + batch * kBatch;
+            bool fast = false;
+            if (TMA) {
+                int l1[kBatch], l2[kBatch];
+                bool staged = true;
+                [[maybe_unused]] double d1d[kBatch], d2d[kBatch];
+                [[maybe_unused]] float d1f[kBatch], d2f[kBatch];
+#pragma unroll
+                for (int e = 0; e < kBatch; ++e) {
+                    int i1, i2;
+                    if (EXACT) {
+                        double row, col;
+                        rect_coord(pe, rtd, h->q2[warp * kLines + batch * kBatch + e], row, col);
+                        lin_floor(row, i1, d1d[e]);
+                        lin_floor(col, i2, d2d[e]);
+                        // lin_floor is only meaningful for 1 <= x < 2^31
+                        const unsigned h1 = (unsigned)__double2hiint(row) - 0x3FF00000u;
+                        const unsigned h2 = (unsigned)__double2hiint(col) - 0x3FF00000u;
+                        staged &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
+                    } else {
+                        float row, col;
+                        rect_coord(pf, rtf, i2f + (float)(batch * kBatch + e), row, col);
+                        lin_floor_fast(row, i1, d1f[e]);
+                        lin_floor_fast(col, i2, d2f[e]);
+                    }
+                    l1[e] = i1 - K1;
+                    l2[e] = i2 - K2;
+                    staged &= ((unsigned)l1[e] < (unsigned)R1) & ((unsigned)l2[e] < (unsigned)R2);
+                }
+                fast = full_lines && __all_sync(0xffffffffu, staged || !a_in);
+                if (fast) {
+                    float a00[kBatch], a10[kBatch], a01[kBatch], a11[kBatch];
+#pragma unroll
+                    for (int e = 0; e < kBatch; ++e) {
+                        const float* q = box + (staged ? l2[e] * box1 + l1[e] : 0);
+                        a00[e] = q[0]; a10[e] = q[1];
+                        a01[e] = q[box1]; a11[e] = q[box1 + 1];
+                    }
+                    float* o = optr;
+#pragma unroll
+                    for (int e = 0; e < kBatch; ++e) {
+                        float v;
+                        if (EXACT)
+                            v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
+                                              (double)a11[e], d1d[e], d2d[e]);
+                        else
+                            v = bilerp_fast(a00[e], a10[e], a01[e], a11[e], d1f[e], d2f[e]);
+                        if (a_in) __stcs(o, v);
+                        o += pitch;
+                    }
+                }
             }
-        }
+            if (!fast) {
+                float* o = optr;
 #pragma unroll
-        for (int e = 0; e < kChunks; ++e) {
-            const int a = a0 + 32 * e;
-            float v = fill;
-            if (ok[e])
-                v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
-                                  d1[e], d2[e]);
-            if (a < g.sz1) __stcs(o + a, v);
+                for (int e = 0; e < kBatch; ++e) {
+                    const int b = bb + e;
+                    if (b < g.sz2 && a_in)
+                        __stcs(o, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b, fill));
+                    o += pitch;
+                }
+            }
+            optr += (long long)kBatch * pitch;
+        }
+        i2f += (float)kT;
+        optr += tile_step;
+        if (TMA) {
+            __syncwarp();
+            if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
+            if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
     }
 }
 
-__global__ void __launch_bounds__(kRectThreads)
-rectify_f32c1_fast(const RectFast p, const RectGeom g, const float* __restrict__ src,
-                   float* __restrict__ dst, float fill) {
-    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * kTile2 + warp;
-    if (b >= g.sz2) return;
-    const float* s = src + (long long)blockIdx.y * g.frame_stride;
-    float* o = dst + (long long)blockIdx.y * g.frame_stride + (long long)b * g.pitch;
-    const ColTermF ct = rect_col_term(p, g.axs1 + b);
-    const unsigned pitch = (unsigned)g.pitch;
-    float i1f = (float)(g.axs0 + lane_id) - p.c1;
-
-    for (int a0 = lane_id; a0 < g.sz1; a0 += kTile1, i1f += (float)kTile1) {
-        unsigned idx[kChunks];
-        bool ok[kChunks];
-        float d1[kChunks], d2[kChunks];
-#pragma unroll
-        for (int e = 0; e < kChunks; ++e) {
-            float row, col;
-            rect_coord(p, ct, i1f + 32.0f * e, row, col);
-            int i1, i2;
-            const bool v1 = lin_pos_fast(row, g.sz1, i1, d1[e]);
-            const bool v2 = lin_pos_fast(col, g.sz2, i2, d2[e]);
-            ok[e] = v1 & v2;
-            idx[e] = (unsigned)i2 * pitch + (unsigned)i1;
-        }
-        float a00[kChunks], a10[kChunks], a01[kChunks], a11[kChunks];
-#pragma unroll
-        for (int e = 0; e < kChunks; ++e) {
-            const float* q = elem_ptr(s, idx[e]);
-            const float* q2 = elem_ptr(s, idx[e] + pitch);
-            if (ok[e]) {
-                a00[e] = __ldg(q);
-                a10[e] = __ldg(q + 1);
-                a01[e] = __ldg(q2);
-                a11[e] = __ldg(q2 + 1);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < kChunks; ++e) {
-            const int a = a0 + 32 * e;
-            float v = fill;
-            if (ok[e]) v = bilerp_fast(a00[e], a10[e], a01[e], a11[e], d1[e], d2[e]);
-            if (a < g.sz1) __stcs(o + a, v);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// u8 x 3 interleaved (RGB{N0f8}), direct gather.  Lane l owns pixels tile + 32*e + l.
-// The two taps of one source line are 6 contiguous bytes at byte offset 3*i: fetched as
-// three aligned 32-bit words and funnelled with PRMT (2 per line) instead of 6 byte loads.
-// A warp's 32 output pixels of one chunk (96 B) are packed through shuffles into
-// 24 aligned 32-bit stores... kept simple here: each lane stores its 3 bytes; the L2
-// merges them (write traffic is still one pass, see profiles/).
-// ---------------------------------------------------------------------------------
+// --------------------------------------------------------------------------------------
+// u8 x 3 interleaved (RGB{N0f8}).  Each tap is 3 bytes at byte offset 3*i; the two taps of
+// one source line are 6 contiguous bytes, fetched as three aligned 32-bit words and
+// funnelled with PRMT.  The staged box is a byte tensor (first axis = 3*pixels).
+// --------------------------------------------------------------------------------------
 struct Taps6 { uint32_t lo, hi; };   // bytes [o, o+4) and [o+4, o+8) of a byte stream
 
-__device__ __forceinline__ Taps6 load6(const uint8_t* __restrict__ base, unsigned o) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (o >> 2);
-    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-    const unsigned sh = o & 3u;
-    const unsigned sel = 0x3210u + 0x1111u * sh;     // bytes sh..sh+3 of the pair
+template <typename LD>
+__device__ __forceinline__ Taps6 load6(const uint32_t* words, unsigned o, LD ld) {
+    const uint32_t* w = words + (o >> 2);
+    const uint32_t w0 = ld(w), w1 = ld(w + 1), w2 = ld(w + 2);
+    const unsigned sel = 0x3210u + 0x1111u * (o & 3u);     // bytes sh..sh+3 of a register pair
     Taps6 t;
     t.lo = __byte_perm(w0, w1, sel);
     t.hi = __byte_perm(w1, w2, sel);
@@ -156,108 +310,179 @@ __device__ __forceinline__ Taps6 load6(const uint8_t* __restrict__ base, unsigne
 __device__ __forceinline__ float byte_f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
 __device__ __forceinline__ double byte_d(uint32_t w, int k) { return (double)((w >> (8 * k)) & 0xffu); }
 
-template <bool EXACT, typename P>
-__global__ void __launch_bounds__(kRectThreads)
-rectify_u8c3_kernel(const P p, const RectGeom g, const uint8_t* __restrict__ src,
-                    uint8_t* __restrict__ dst, uchar3 fill, unsigned src_bytes) {
+template <bool EXACT, bool TMA>
+__global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads)
+rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
+                    const RectGeom g, const TileCfg cfg, const uint8_t* __restrict__ src,
+                    uint8_t* __restrict__ dst, uchar3 fill, unsigned frame_bytes) {
+    extern __shared__ __align__(128) uint8_t stage_mem[];
+    __shared__ SmemCtl ctl;
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y * kTile2 + warp;
-    if (b >= g.sz2) return;
-    const int a_base = blockIdx.x * kTile1 + lane_id;
-    const uint8_t* s = src + (long long)blockIdx.z * g.frame_stride * 3;
-    uint8_t* o = dst + ((long long)blockIdx.z * g.frame_stride + (long long)b * g.pitch) * 3;
-    const auto ct = rect_col_term(p, g.axs1 + b);
-    const unsigned pitch3 = (unsigned)g.pitch * 3u;
-    // the word-granular gather may read up to 5 bytes past the last needed byte: stay
-    // inside the caller's buffer by taking the byte path for the few taps at its very end
-    const unsigned frame_off = (unsigned)((reinterpret_cast<uintptr_t>(s)) & 3u);
-    const uint8_t* s4 = s - frame_off;                       // 4-byte aligned base
-    const unsigned safe_end = src_bytes;                     // bytes of this frame reachable from s
+    const int a_lo = blockIdx.x * kT;
+    const int frame = blockIdx.z;
+    const int t_begin = blockIdx.y * cfg.tiles_per_seg;
+    const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
+    pipeline_init(&ctl, cfg.stages, TMA);
 
-    float i1f0 = 0.f;
-    if constexpr (!EXACT) i1f0 = (float)(g.axs0 + a_base) - p.c1;
+    if (TMA && warp == kWarps) {
+        if (lane_id == 0) tma_prefetch_desc(&tmap);
+        for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
+            const int s = it % cfg.stages;
+            mbar_wait(&ctl.empty[s], ((it / cfg.stages) & 1) ^ 1);
+            producer_tile<EXACT, 3>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
+                                    s, a_lo, tile, frame, lane_id);
+        }
+        return;
+    }
+
+    const int a = a_lo + lane_id;
+    const uint8_t* sframe = src + (long long)frame * g.frame_stride * 3;
+    uint8_t* ocol = dst + ((long long)frame * g.frame_stride + a) * 3;
+    const unsigned pitch3 = (unsigned)g.pitch * 3u;
+    const unsigned box_pitch = (unsigned)cfg.box1 * 3u;           // bytes per box line (multiple of 16)
+    // word-granular global gather: 4-byte aligned base, and the byte path for the last
+    // few taps of the frame so nothing outside the caller's buffer is touched
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(sframe) & 3u);
+    const uint32_t* gwords = reinterpret_cast<const uint32_t*>(sframe - mis);
+    RowTermD rtd;
+    RowTermF rtf;
+    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+    auto ld_global = [](const uint32_t* p) { return __ldg(p); };
+    auto ld_shared = [](const uint32_t* p) { return *p; };
+
+    for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
+        const int s = it % cfg.stages;
+        const int b0 = tile * kT + warp * kLines;
+        int K1 = 0, R1 = 0, K2 = 0, R2 = 0;
+        const uint32_t* box = nullptr;
+        unsigned box_off = 0;
+        const StageHdr* h = &ctl.hdr[s];
+        if (TMA) {
+            mbar_wait(&ctl.full[s], (it / cfg.stages) & 1);
+            K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
+            box = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)s * cfg.box_bytes);
+            box_off = (unsigned)h->base_off * 3u;   // base_off = lo2*box1 + lo1 (pixels)
+        }
 #pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        const int a = a_base + 32 * e;
-        uint32_t r = fill.x, gg = fill.y, bb = fill.z;
-        int i1, i2;
-        bool ok;
-        [[maybe_unused]] double d1d, d2d;
-        [[maybe_unused]] float d1f, d2f;
-        if constexpr (EXACT) {
-            double row, col;
-            rect_coord(p, ct, g.axs0 + a, row, col);
-            const bool v1 = lin_pos(row, g.sz1, i1, d1d);
-            const bool v2 = lin_pos(col, g.sz2, i2, d2d);
-            ok = v1 & v2;
-        } else {
-            float row, col;
-            rect_coord(p, ct, i1f0 + 32.0f * e, row, col);
-            const bool v1 = lin_pos_fast(row, g.sz1, i1, d1f);
-            const bool v2 = lin_pos_fast(col, g.sz2, i2, d2f);
-            ok = v1 & v2;
-        }
-        if (ok) {
-            const unsigned off = (unsigned)i2 * pitch3 + (unsigned)i1 * 3u + frame_off;
+        for (int e = 0; e < kLines; ++e) {
+            const int b = b0 + e;
+            if (b >= g.sz2) continue;
+            int i1, i2;
+            bool staged = false, have = false;
             Taps6 t0, t1;
-            if (off + pitch3 + 12u <= safe_end + frame_off) {
-                t0 = load6(s4, off);
-                t1 = load6(s4, off + pitch3);
-            } else {                                          // last bytes of the buffer
-                const uint8_t* q = s4 + off;
-                t0.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-                t0.hi = q[4] | (q[5] << 8);
-                q += pitch3;
-                t1.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-                t1.hi = q[4] | (q[5] << 8);
-            }
-            // t.lo = [a00.r a00.g a00.b a10.r], t.hi = [a10.g a10.b . .]
-            if constexpr (EXACT) {
-                r  = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 0), byte_d(t0.lo, 3), byte_d(t1.lo, 0), byte_d(t1.lo, 3), d1d, d2d));
-                gg = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 1), byte_d(t0.hi, 0), byte_d(t1.lo, 1), byte_d(t1.hi, 0), d1d, d2d));
-                bb = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 2), byte_d(t0.hi, 1), byte_d(t1.lo, 2), byte_d(t1.hi, 1), d1d, d2d));
+            t0.lo = t0.hi = t1.lo = t1.hi = 0;
+            [[maybe_unused]] double rowd, cold, d1d, d2d;
+            [[maybe_unused]] float d1f, d2f;
+            if (EXACT) {
+                const double q2 = TMA ? h->q2[warp * kLines + e] : rect_q2(pe, g.axs1 + b);
+                rect_coord(pe, rtd, q2, rowd, cold);
+                lin_floor(rowd, i1, d1d);
+                lin_floor(cold, i2, d2d);
             } else {
-                r  = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 0), byte_f(t0.lo, 3), byte_f(t1.lo, 0), byte_f(t1.lo, 3), d1f, d2f));
-                gg = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 1), byte_f(t0.hi, 0), byte_f(t1.lo, 1), byte_f(t1.hi, 0), d1f, d2f));
-                bb = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 2), byte_f(t0.hi, 1), byte_f(t1.lo, 2), byte_f(t1.hi, 1), d1f, d2f));
-                r = min(r, 255u); gg = min(gg, 255u); bb = min(bb, 255u);
+                float row, col;
+                rect_coord(pf, rtf, (float)(g.axs1 + b) - pf.c2, row, col);
+                lin_floor_fast(row, i1, d1f);
+                lin_floor_fast(col, i2, d2f);
+            }
+            if (TMA) {
+                const int l1 = i1 - K1, l2 = i2 - K2;
+                staged = ((unsigned)l1 < (unsigned)R1) & ((unsigned)l2 < (unsigned)R2);
+                if (EXACT) {
+                    const unsigned h1 = (unsigned)__double2hiint(rowd) - 0x3FF00000u;
+                    const unsigned h2 = (unsigned)__double2hiint(cold) - 0x3FF00000u;
+                    staged &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
+                }
+                if (staged) {
+                    const unsigned o = box_off + (unsigned)l2 * box_pitch + (unsigned)l1 * 3u;
+                    t0 = load6(box, o, ld_shared);
+                    t1 = load6(box, o + box_pitch, ld_shared);
+                    have = true;
+                }
+            }
+            if (!staged) {
+                bool ok;
+                int g1, g2;
+                if (EXACT) {
+                    ok = lin_ok(rowd, g.sz1) & lin_ok(cold, g.sz2);
+                    g1 = i1; g2 = i2;
+                    lin_fix_edge(g.sz1, g1, d1d);
+                    lin_fix_edge(g.sz2, g2, d2d);
+                    g1 -= 1; g2 -= 1;
+                } else {
+                    g1 = i1 - (kMagicBits + 1); g2 = i2 - (kMagicBits + 1);
+                    ok = ((unsigned)g1 <= (unsigned)(g.sz1 - 2)) & ((unsigned)g2 <= (unsigned)(g.sz2 - 2));
+                }
+                if (ok) {
+                    const unsigned off = (unsigned)g2 * pitch3 + (unsigned)g1 * 3u;
+                    if (off + pitch3 + 12u <= frame_bytes) {
+                        t0 = load6(gwords, off + mis, ld_global);
+                        t1 = load6(gwords, off + pitch3 + mis, ld_global);
+                    } else {                                   // last bytes of the frame
+                        const uint8_t* q = sframe + off;
+                        t0.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+                        t0.hi = q[4] | (q[5] << 8);
+                        q += pitch3;
+                        t1.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+                        t1.hi = q[4] | (q[5] << 8);
+                    }
+                    have = true;
+                }
+            }
+            uint32_t r = fill.x, gg = fill.y, bb = fill.z;
+            if (have) {
+                // t.lo = [a00.r a00.g a00.b a10.r], t.hi = [a10.g a10.b . .]
+                if (EXACT) {
+                    r  = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 0), byte_d(t0.lo, 3), byte_d(t1.lo, 0), byte_d(t1.lo, 3), d1d, d2d));
+                    gg = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 1), byte_d(t0.hi, 0), byte_d(t1.lo, 1), byte_d(t1.hi, 0), d1d, d2d));
+                    bb = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 2), byte_d(t0.hi, 1), byte_d(t1.lo, 2), byte_d(t1.hi, 1), d1d, d2d));
+                } else {
+                    r  = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 0), byte_f(t0.lo, 3), byte_f(t1.lo, 0), byte_f(t1.lo, 3), d1f, d2f));
+                    gg = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 1), byte_f(t0.hi, 0), byte_f(t1.lo, 1), byte_f(t1.hi, 0), d1f, d2f));
+                    bb = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 2), byte_f(t0.hi, 1), byte_f(t1.lo, 2), byte_f(t1.hi, 1), d1f, d2f));
+                    r = min(r, 255u); gg = min(gg, 255u); bb = min(bb, 255u);
+                }
+            }
+            if (a < g.sz1) {
+                uint8_t* q = ocol + (long long)b * g.pitch * 3;
+                q[0] = (uint8_t)r; q[1] = (uint8_t)gg; q[2] = (uint8_t)bb;
             }
         }
-        if (a < g.sz1) {
-            uint8_t* q = o + 3 * a;
-            q[0] = (uint8_t)r; q[1] = (uint8_t)gg; q[2] = (uint8_t)bb;
+        if (TMA) {
+            __syncwarp();
+            if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
         }
     }
 }
 
-// ---------------------------------------------------------------------------------
+// --------------------------------------------------------------------------------------
 // the map alone (FP64): the source coordinate each output pixel samples
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRectThreads)
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kConsumerThreads)
 rectify_map_kernel(const RectExact p, const RectGeom g, double* __restrict__ map_row,
                    double* __restrict__ map_col) {
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y * kTile2 + warp;
-    if (b >= g.sz2) return;
-    const ColTermD ct = rect_col_term(p, g.axs1 + b);
+    const int a = blockIdx.x * kT + lane_id;
+    if (a >= g.sz1) return;
+    const RowTermD rt = rect_row_term(p, g.axs0 + a);
 #pragma unroll
-    for (int e = 0; e < kChunks; ++e) {
-        const int a = blockIdx.x * kTile1 + 32 * e + lane_id;
-        if (a < g.sz1) {
+    for (int e = 0; e < kLines; ++e) {
+        const int b = blockIdx.y * kT + warp * kLines + e;
+        if (b < g.sz2) {
             double row, col;
-            rect_coord(p, ct, g.axs0 + a, row, col);
+            rect_coord(p, rt, rect_q2(p, g.axs1 + b), row, col);
             map_row[(long long)b * g.pitch + a] = row;
             map_col[(long long)b * g.pitch + a] = col;
         }
     }
 }
 
-// ---------------------------------------------------------------------------------
-// host launchers
-// ---------------------------------------------------------------------------------
+// --------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------
 static RectGeom make_geom(const int64_t axs_min[2], int sz1, int sz2, size_t pitch,
                           size_t frame_stride, int nframes) {
     RectGeom g;
+    memset(&g, 0, sizeof(g));
     g.axs0 = (int)axs_min[0]; g.axs1 = (int)axs_min[1];
     g.sz1 = sz1; g.sz2 = sz2; g.pitch = (long long)pitch; g.frame_stride = (long long)frame_stride;
     g.nframes = nframes;
@@ -278,8 +503,8 @@ static RectExact make_exact(const ChainD& ch, double ratio) {
 static RectFast make_fast(const ChainD& ch, double ratio, const RectGeom& g) {
     RectFast p;
     const double sc = (1.0 / ratio) * ch.inv_cs;
-    const double c1 = (double)g.axs0 + 0.5 * (g.sz1 - 1), c2 = (double)g.axs1 + 0.5 * (g.sz2 - 1);
-    const double c1r = std::nearbyint(c1), c2r = std::nearbyint(c2);
+    const double c1r = std::nearbyint((double)g.axs0 + 0.5 * (g.sz1 - 1));
+    const double c2r = std::nearbyint((double)g.axs1 + 0.5 * (g.sz2 - 1));
     for (int i = 0; i < 3; ++i) {
         const double A = ch.R[3 * i] * sc, C = ch.R[3 * i + 1] * sc;
         p.A[i] = (float)A; p.Cc[i] = (float)C;
@@ -307,8 +532,143 @@ int check_rect_args(const int64_t axs_min[2], int sz1, int sz2, size_t pitch, si
     return CC_OK;
 }
 
-static dim3 rect_grid(int sz1, int sz2, int nframes) {
-    return dim3((sz1 + kTile1 - 1) / kTile1, (sz2 + kTile2 - 1) / kTile2, nframes);
+// host evaluation of the map (double) for the box-size estimate only
+static void host_coord(const ChainD& ch, double inv_ratio, long long I1, long long I2, double* row,
+                       double* col) {
+    const double q1 = ((double)I1 * inv_ratio) * ch.inv_cs, q2 = ((double)I2 * inv_ratio) * ch.inv_cs;
+    const double P1 = ch.R[1] * q2 + (ch.R[0] * q1 + ch.t[0]);
+    const double P2 = ch.R[4] * q2 + (ch.R[3] * q1 + ch.t[1]);
+    const double P3 = ch.R[7] * q2 + (ch.R[6] * q1 + ch.t[2]);
+    const double u = P1 / P3, v = P2 / P3;
+    const double radial = 1.0 + ch.k * (u * u + v * v);
+    *row = ch.frow * radial * u + ch.crow;
+    *col = ch.fcol * radial * v + ch.ccol;
+}
+
+// Largest source footprint of any 32x32 output tile that touches the frame, from the tile
+// corners (the kernel positions each box from the same four corners).  Cached: a video
+// stream calls with the same calibration over and over.
+struct PlanKey { ChainD ch; double ratio; RectGeom g; };
+struct Plan { PlanKey key; bool valid; int need1, need2; };
+static Plan g_plan_cache[8];
+static int g_plan_next = 0;
+static std::mutex g_plan_mutex;
+
+static void footprint(const ChainD& ch, double ratio, const RectGeom& g, int* need1, int* need2) {
+    const double inv_ratio = 1.0 / ratio;
+    const int n1 = (g.sz1 + kT - 1) / kT, n2 = (g.sz2 + kT - 1) / kT;
+    int m1 = 0, m2 = 0;
+    for (int t2 = 0; t2 < n2; ++t2) {
+        const int b_lo = t2 * kT, b_hi = std::min(b_lo + kT - 1, g.sz2 - 1);
+        for (int t1 = 0; t1 < n1; ++t1) {
+            const int a_lo = t1 * kT, a_hi = std::min(a_lo + kT - 1, g.sz1 - 1);
+            double r[4], c[4];
+            host_coord(ch, inv_ratio, g.axs0 + a_lo, g.axs1 + b_lo, &r[0], &c[0]);
+            host_coord(ch, inv_ratio, g.axs0 + a_hi, g.axs1 + b_lo, &r[1], &c[1]);
+            host_coord(ch, inv_ratio, g.axs0 + a_lo, g.axs1 + b_hi, &r[2], &c[2]);
+            host_coord(ch, inv_ratio, g.axs0 + a_hi, g.axs1 + b_hi, &r[3], &c[3]);
+            double rmin = r[0], rmax = r[0], cmin = c[0], cmax = c[0];
+            bool finite = true;
+            for (int i = 0; i < 4; ++i) {
+                finite = finite && std::isfinite(r[i]) && std::isfinite(c[i]);
+                rmin = std::min(rmin, r[i]); rmax = std::max(rmax, r[i]);
+                cmin = std::min(cmin, c[i]); cmax = std::max(cmax, c[i]);
+            }
+            // tiles entirely outside the frame never gather
+            if (!finite || rmax < 1.0 || cmax < 1.0 || rmin > g.sz1 || cmin > g.sz2) continue;
+            m1 = std::max(m1, (int)(std::floor(rmax) - std::floor(rmin)));
+            m2 = std::max(m2, (int)(std::floor(cmax) - std::floor(cmin)));
+        }
+    }
+    // taps floor-1 .. floor; 2 texels of slack below (origin) and 1 above
+    *need1 = m1 + 2 + 3;
+    *need2 = m2 + 2 + 3;
+}
+
+static void plan_lookup(const ChainD& ch, double ratio, const RectGeom& g, int* need1, int* need2) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
+    for (auto& p : g_plan_cache)
+        if (p.valid && memcmp(&p.key, &key, sizeof(key)) == 0) { *need1 = p.need1; *need2 = p.need2; return; }
+    footprint(ch, ratio, g, need1, need2);
+    Plan& p = g_plan_cache[g_plan_next++ % 8];
+    p.key = key; p.valid = true; p.need1 = *need1; p.need2 = *need2;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encoder(cc_ctx* ctx) {
+    if (!ctx->encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            ctx->encode_tiled = fn;
+    }
+    return reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+}
+
+// Decide whether the TMA-staged variant applies and build its tensor map + tile config.
+// pxb: bytes per pixel (4: one float element; 3: three u8 elements).
+static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom& g, const void* src,
+                     int pxb, CUtensorMap* tmap, TileCfg* cfg) {
+    const size_t pitch_b = (size_t)g.pitch * pxb, frame_b = (size_t)g.frame_stride * pxb;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) || (pitch_b & 15u) || (g.nframes > 1 && (frame_b & 15u)))
+        return false;
+    EncodeTiledFn enc = encoder(ctx);
+    if (!enc) return false;
+    int need1, need2;
+    plan_lookup(ch, ratio, g, &need1, &need2);
+    // box1 in pixels with a byte length that is a multiple of 16; the stage size must be a
+    // multiple of 128 bytes so every stage base stays 128-byte aligned
+    const int unit = (pxb == 4) ? 4 : 16;
+    // (+ unit - 1: the kernel rounds the box origin down to a multiple of `unit` pixels)
+    const int box1 = (need1 + unit - 1 + unit - 1) / unit * unit;
+    int box2 = need2;
+    while (((size_t)box1 * pxb * box2) % 128) ++box2;
+    const int box1_elems = (pxb == 4) ? box1 : box1 * 3;
+    if (box1_elems > 256 || box2 > 256) return false;
+    const int box_bytes = box1 * pxb * box2;
+    if (box_bytes > 40 * 1024) return false;     // footprint too large to be worth staging
+    int stages = 3;
+    while (stages > 2 && stages * box_bytes > 56 * 1024) --stages;
+
+    cuuint64_t dims[3] = {(cuuint64_t)g.sz1 * (pxb == 4 ? 1 : 3), (cuuint64_t)g.sz2,
+                          (cuuint64_t)std::max(g.nframes, 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch_b, (cuuint64_t)(g.nframes > 1 ? frame_b : pitch_b * g.sz2)};
+    cuuint32_t box[3] = {(cuuint32_t)box1_elems, (cuuint32_t)box2, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(tmap, pxb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                           const_cast<void*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    cfg->box1 = box1; cfg->box2 = box2; cfg->stages = stages; cfg->box_bytes = box_bytes;
+    return true;
+}
+
+static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips) {
+    cfg->ntiles2 = (g.sz2 + kT - 1) / kT;
+    // enough CTAs for ~6 waves of 4 CTAs/SM, but walks long enough to amortise the thread setup
+    const long long ctas_wanted = (long long)ctx->sm_count * 4 * 6;
+    const long long per_seg = (long long)strips * std::max(g.nframes, 1);
+    long long segs = (ctas_wanted + per_seg - 1) / per_seg;
+    if (segs < 1) segs = 1;
+    int tps = (int)((cfg->ntiles2 + segs - 1) / segs);
+    if (tps < 4) tps = std::min(4, cfg->ntiles2);
+    cfg->tiles_per_seg = std::max(tps, 1);
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        CC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CC_OK;
 }
 
 int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int64_t axs_min[2],
@@ -316,13 +676,34 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
                          size_t frame_stride, int nframes, float fill, unsigned flags,
                          cudaStream_t st) {
     if (nframes == 0) return CC_OK;
-    CC_REQUIRE((flags & CC_GATHER_TMA) == 0, "TMA gather not available for this layout");
-    const dim3 grid((sz2 + kTile2 - 1) / kTile2, nframes);
     const RectGeom g = make_geom(axs_min, sz1, sz2, pitch, frame_stride, nframes);
-    if (flags & CC_COORD_F32)
-        rectify_f32c1_fast<<<grid, kRectThreads, 0, st>>>(make_fast(chd, ratio, g), g, src, dst, fill);
-    else
-        rectify_f32c1_exact<<<grid, kRectThreads, 0, st>>>(make_exact(chd, ratio), g, src, dst, fill);
+    const RectExact pe = make_exact(chd, ratio);
+    const RectFast pf = make_fast(chd, ratio, g);
+    const bool exact = !(flags & CC_COORD_F32);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    TileCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, &tmap, &cfg);
+    if ((flags & CC_GATHER_TMA) && !tma)
+        return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
+    const int strips = (sz1 + kT - 1) / kT;
+    if (!tma) cfg.stages = 1;
+    fill_cfg(&cfg, g, ctx, strips);
+    const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
+    const size_t smem = tma ? (size_t)cfg.stages * cfg.box_bytes : 0;
+    int rc = CC_OK;
+    if (tma && exact) {
+        if ((rc = set_smem(rectify_f32c1_kernel<true, true>, smem))) return rc;
+        rectify_f32c1_kernel<true, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+    } else if (tma) {
+        if ((rc = set_smem(rectify_f32c1_kernel<false, true>, smem))) return rc;
+        rectify_f32c1_kernel<false, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+    } else if (exact) {
+        rectify_f32c1_kernel<true, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+    } else {
+        rectify_f32c1_kernel<false, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+    }
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
     return CC_OK;
@@ -333,16 +714,37 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
                         size_t frame_stride, int nframes, const uint8_t fill[3], unsigned flags,
                         cudaStream_t st) {
     if (nframes == 0) return CC_OK;
-    CC_REQUIRE((flags & CC_GATHER_TMA) == 0, "TMA gather not available for this layout");
-    const dim3 grid = rect_grid(sz1, sz2, nframes);
     const RectGeom g = make_geom(axs_min, sz1, sz2, pitch, frame_stride, nframes);
+    const RectExact pe = make_exact(chd, ratio);
+    const RectFast pf = make_fast(chd, ratio, g);
+    const bool exact = !(flags & CC_COORD_F32);
     const uchar3 f = make_uchar3(fill[0], fill[1], fill[2]);
     // bytes of one frame that belong to the caller: the last line is only sz1 pixels long
     const unsigned frame_bytes = (unsigned)((pitch * (size_t)(sz2 - 1) + (size_t)sz1) * 3);
-    if (flags & CC_COORD_F32)
-        rectify_u8c3_kernel<false, RectFast><<<grid, kRectThreads, 0, st>>>(make_fast(chd, ratio, g), g, src, dst, f, frame_bytes);
-    else
-        rectify_u8c3_kernel<true, RectExact><<<grid, kRectThreads, 0, st>>>(make_exact(chd, ratio), g, src, dst, f, frame_bytes);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    TileCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 3, &tmap, &cfg);
+    if ((flags & CC_GATHER_TMA) && !tma)
+        return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
+    const int strips = (sz1 + kT - 1) / kT;
+    if (!tma) cfg.stages = 1;
+    fill_cfg(&cfg, g, ctx, strips);
+    const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
+    const size_t smem = tma ? (size_t)cfg.stages * cfg.box_bytes : 0;
+    int rc = CC_OK;
+    if (tma && exact) {
+        if ((rc = set_smem(rectify_u8c3_kernel<true, true>, smem))) return rc;
+        rectify_u8c3_kernel<true, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
+    } else if (tma) {
+        if ((rc = set_smem(rectify_u8c3_kernel<false, true>, smem))) return rc;
+        rectify_u8c3_kernel<false, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
+    } else if (exact) {
+        rectify_u8c3_kernel<true, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
+    } else {
+        rectify_u8c3_kernel<false, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
+    }
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
     return CC_OK;
@@ -352,8 +754,8 @@ int launch_rectify_map(cc_ctx* ctx, const ChainD& chd, double ratio, const int64
                        double* map_row, double* map_col, int sz1, int sz2, size_t pitch,
                        cudaStream_t st) {
     const RectGeom g = make_geom(axs_min, sz1, sz2, pitch, pitch * (size_t)sz2, 1);
-    rectify_map_kernel<<<rect_grid(sz1, sz2, 1), kRectThreads, 0, st>>>(make_exact(chd, ratio), g,
-                                                                        map_row, map_col);
+    const dim3 grid((sz1 + kT - 1) / kT, (sz2 + kT - 1) / kT);
+    rectify_map_kernel<<<grid, kConsumerThreads, 0, st>>>(make_exact(chd, ratio), g, map_row, map_col);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
     return CC_OK;

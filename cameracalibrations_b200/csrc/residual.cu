@@ -93,9 +93,9 @@ __device__ __forceinline__ void corner_jac(const ViewGeom& g, const double t[3],
                                            double X0, double X1, double X2, double obs_r,
                                            double obs_c, double res[2], double J[2][10]) {
     const double q0 = X0 * in.inv_cs, q1 = X1 * in.inv_cs, q2 = X2 * in.inv_cs;
-    const double P0 = fma(g.R[0], q0, fma(g.R[1], q1, fma(g.R[2], q2, t[0])));
-    const double P1 = fma(g.R[3], q0, fma(g.R[4], q1, fma(g.R[5], q2, t[1])));
-    const double P2 = fma(g.R[6], q0, fma(g.R[7], q1, fma(g.R[8], q2, t[2])));
+    const double P0 = fma(g.R[1], q1, fma(g.R[0], q0, fma(g.R[2], q2, t[0])));
+    const double P1 = fma(g.R[4], q1, fma(g.R[3], q0, fma(g.R[5], q2, t[1])));
+    const double P2 = fma(g.R[7], q1, fma(g.R[6], q0, fma(g.R[8], q2, t[2])));
     const double s = 1.0 / P2;
     const double u = P0 * s, v = P1 * s;
     const double r2 = fma(v, v, u * u);

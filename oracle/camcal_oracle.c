@@ -133,9 +133,11 @@ void cco_world2img(const cco_chain *ch, double x, double y, double z,
     double q1 = x * ch->inv_cs, q2 = y * ch->inv_cs, q3 = z * ch->inv_cs;
     /* extrinsic: R q + t */
     const double *R = ch->R;
-    double P1 = fma(R[0], q1, fma(R[1], q2, fma(R[2], q3, ch->t[0])));
-    double P2 = fma(R[3], q1, fma(R[4], q2, fma(R[5], q3, ch->t[1])));
-    double P3 = fma(R[6], q1, fma(R[7], q2, fma(R[8], q3, ch->t[2])));
+    /* order: z term, then the first world axis, then the second (the rectification
+     * kernels keep the first-axis term per thread and add the second per pixel) */
+    double P1 = fma(R[1], q2, fma(R[0], q1, fma(R[2], q3, ch->t[0])));
+    double P2 = fma(R[4], q2, fma(R[3], q1, fma(R[5], q3, ch->t[1])));
+    double P3 = fma(R[7], q2, fma(R[6], q1, fma(R[8], q3, ch->t[2])));
     /* PerspectiveMap: scale = 1/v[3]; (v[1]*scale, v[2]*scale) */
     double s = 1.0 / P3;
     double u = P1 * s, v = P2 * s;
@@ -405,7 +407,7 @@ static void corner_jac(const double R[9], const double dR[3][9], const double t[
     double q[3] = {X[0] * inv_cs, X[1] * inv_cs, X[2] * inv_cs};
     double P[3];
     for (int i = 0; i < 3; ++i)
-        P[i] = fma(R[3 * i], q[0], fma(R[3 * i + 1], q[1], fma(R[3 * i + 2], q[2], t[i])));
+        P[i] = fma(R[3 * i + 1], q[1], fma(R[3 * i], q[0], fma(R[3 * i + 2], q[2], t[i])));
     double s = 1.0 / P[2];
     double u = P[0] * s, v = P[1] * s;
     double r2 = fma(v, v, u * u);

@@ -3,15 +3,14 @@
 """
 import csv, io, re, subprocess, sys, collections
 rep, kname = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", kname],
-                     capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 out, started = [], False
 for r in rows:
     if r and r[0] == "Kernel Name":
         if started:
             break
-        started = kname in r[1]
+        started = kname in r[1].replace("(bool)", "")
         continue
     if started and len(r) > 6 and r[0].startswith("0x"):
         out.append((r[1].strip(), int(r[5]), int(r[4])))

@@ -209,6 +209,15 @@ def test_rectify_f32c1_bit_exact(cc, sz):
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     ok = ~np.isnan(ref)
     assert np.array_equal(got[ok], ref[ok])               # bit-exact
+    # the TMA-staged and the direct gather are the same function
+    got_d = cc.warp(c, 0, _dev(frames), ratio, axs, gather="direct").cpu().numpy()
+    assert np.array_equal(np.nan_to_num(got_d, nan=-7.0), np.nan_to_num(got, nan=-7.0))
+    if sz[0] % 4 == 0:                                    # TMA needs a 16-byte multiple pitch
+        got_t = cc.warp(c, 0, _dev(frames), ratio, axs, gather="tma").cpu().numpy()
+        assert np.array_equal(np.nan_to_num(got_t, nan=-7.0), np.nan_to_num(got, nan=-7.0))
+    else:
+        with pytest.raises(cc.CamcalError):
+            cc.warp(c, 0, _dev(frames), ratio, axs, gather="tma")
     if sz[1] >= 77:
         assert 0.3 < ok.mean()
     # the map itself: bit-exact source coordinates => bit-exact indices and weights
@@ -232,8 +241,35 @@ def test_rectify_u8c3_bit_exact(cc, sz):
     ref = oc.rectify_u8c3(ch, 1.0 / ratio, axs, frames, fill=(1, 2, 3))
     got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(1, 2, 3)).cpu().numpy()
     assert np.array_equal(got, ref)
+    got_d = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(1, 2, 3), gather="direct").cpu().numpy()
+    assert np.array_equal(got_d, ref)
+    if sz[0] % 16 == 0:
+        got_t = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(1, 2, 3), gather="tma").cpu().numpy()
+        assert np.array_equal(got_t, ref)
     got_h = cc.warp(c, 0, frames, ratio, axs, fill=(1, 2, 3))
     assert np.array_equal(got_h, ref)
+
+
+def test_rectify_tilted_views_staged_and_fallback(cc, example_fit):
+    """The reference's own example views are tilted up to 0.8 rad: tile footprints reach 75 x 75
+    texels, some exceed the staged box -> those pixels take the direct path inside the TMA
+    kernel.  Every view, both pixel formats, both coordinate modes' fill decisions."""
+    intr = example_fit["intr_tuple"]
+    n1, n2 = example_fit["n_corners"]
+    sz = (376, 500)                                    # 376: 16-byte multiple pitch for fp32
+    c = _calib(cc, intr, example_fit["view_list"], example_fit["files"])
+    rng = np.random.default_rng(11)
+    frames = rng.random((2, sz[1], sz[0]), dtype=np.float32)
+    for vi, (rv, tv) in enumerate(example_fit["view_list"]):
+        ip = example_fit["corners_np"][vi].reshape(n2, n1, 2).transpose(1, 0, 2)
+        ratio, axs = cc.image_transformations(c, vi, [example_fit["corners_np"][i].reshape(n2, n1, 2).transpose(1, 0, 2) for i in range(6)], 1.0, (n1, n2), sz)
+        assert ratio == oc.get_ratio(ip, 1.0)
+        ch = oc.chain(intr, rv, tv)
+        ref = oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-2.0)
+        for gather in ("auto", "direct"):
+            got = cc.warp(c, vi, _dev(frames), ratio, axs, fill=-2.0, gather=gather).cpu().numpy()
+            assert np.array_equal(got, ref), (vi, gather)
+        assert (ref != -2.0).mean() > 0.2
 
 
 def test_rectify_edge_rule(cc):
