@@ -194,7 +194,8 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact p
     const int box1 = cfg.box1;
     RowTermD rtd;
     RowTermF rtf;
-    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+    const int a_c = min(a, g.sz1 - 1);                 // out-of-frame lanes shadow the last pixel
+    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
     const int line0 = t_begin * kT + warp * kLines;
     float* optr = dst + (long long)frame * g.frame_stride + (long long)line0 * g.pitch + a;
     float i2f = (float)(g.axs1 + line0) - pf.c2;       // fast path: second-axis index, advanced per line
@@ -208,62 +209,82 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact p
         int K1 = 0, R1 = 0, K2 = 0, R2 = 0;
         const float* box = nullptr;
         const StageHdr* h = &ctl.hdr[s];
-        if (TMA) {
-            mbar_wait(&ctl.full[s], phase);
-            K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
-            box = reinterpret_cast<const float*>(stage_mem + (size_t)s * cfg.box_bytes) + h->base_off;
-        }
 #pragma unroll
         for (int batch = 0; batch < kLines / kBatch; ++batch) {
             const int bb = b0 + batch * kBatch;
             bool fast = false;
             if (TMA) {
-                int l1[kBatch], l2[kBatch];
-                bool staged = true;
+                // coordinates first: they do not depend on the staged box, so the TMA
+                // latency of this tile hides behind them
+                int t1[kBatch], t2[kBatch];
+                bool guard = true;
                 [[maybe_unused]] double d1d[kBatch], d2d[kBatch];
-                [[maybe_unused]] float d1f[kBatch], d2f[kBatch];
+                [[maybe_unused]] float2 d1p[kBatch / 2], d2p[kBatch / 2];
+                if (EXACT) {
+                    if (batch == 0) mbar_wait(&ctl.full[s], phase);   // q2 comes from the header
 #pragma unroll
-                for (int e = 0; e < kBatch; ++e) {
-                    int i1, i2;
-                    if (EXACT) {
+                    for (int e = 0; e < kBatch; ++e) {
                         double row, col;
                         rect_coord(pe, rtd, h->q2[warp * kLines + batch * kBatch + e], row, col);
-                        lin_floor(row, i1, d1d[e]);
-                        lin_floor(col, i2, d2d[e]);
+                        lin_floor(row, t1[e], d1d[e]);
+                        lin_floor(col, t2[e], d2d[e]);
                         // lin_floor is only meaningful for 1 <= x < 2^31
                         const unsigned h1 = (unsigned)__double2hiint(row) - 0x3FF00000u;
                         const unsigned h2 = (unsigned)__double2hiint(col) - 0x3FF00000u;
-                        staged &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
-                    } else {
-                        float row, col;
-                        rect_coord(pf, rtf, i2f + (float)(batch * kBatch + e), row, col);
-                        lin_floor_fast(row, i1, d1f[e]);
-                        lin_floor_fast(col, i2, d2f[e]);
+                        guard &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
                     }
-                    l1[e] = i1 - K1;
-                    l2[e] = i2 - K2;
+                } else {
+#pragma unroll
+                    for (int hh = 0; hh < kBatch / 2; ++hh) {
+                        float2 row, col;
+                        const float base = i2f + (float)(batch * kBatch + 2 * hh);
+                        rect_coord2(pf, rtf, make_float2(base, base + 1.0f), row, col);
+                        lin_floor_fast2(row, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
+                        lin_floor_fast2(col, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
+                    }
+                }
+                if (batch == 0) {
+                    if (!EXACT) mbar_wait(&ctl.full[s], phase);
+                    K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
+                    box = reinterpret_cast<const float*>(stage_mem + (size_t)s * cfg.box_bytes) + h->base_off;
+                }
+                int l1[kBatch], l2[kBatch];
+                bool staged = guard;
+#pragma unroll
+                for (int e = 0; e < kBatch; ++e) {
+                    l1[e] = t1[e] - K1;
+                    l2[e] = t2[e] - K2;
                     staged &= ((unsigned)l1[e] < (unsigned)R1) & ((unsigned)l2[e] < (unsigned)R2);
                 }
-                fast = full_lines && __all_sync(0xffffffffu, staged || !a_in);
+                fast = full_lines && __all_sync(0xffffffffu, staged);
                 if (fast) {
                     float a00[kBatch], a10[kBatch], a01[kBatch], a11[kBatch];
 #pragma unroll
                     for (int e = 0; e < kBatch; ++e) {
-                        const float* q = box + (staged ? l2[e] * box1 + l1[e] : 0);
+                        const float* q = box + (l2[e] * box1 + l1[e]);
                         a00[e] = q[0]; a10[e] = q[1];
                         a01[e] = q[box1]; a11[e] = q[box1 + 1];
                     }
                     float* o = optr;
+                    if (EXACT) {
 #pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        float v;
-                        if (EXACT)
-                            v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
-                                              (double)a11[e], d1d[e], d2d[e]);
-                        else
-                            v = bilerp_fast(a00[e], a10[e], a01[e], a11[e], d1f[e], d2f[e]);
-                        if (a_in) __stcs(o, v);
-                        o += pitch;
+                        for (int e = 0; e < kBatch; ++e) {
+                            const float v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
+                                                          (double)a11[e], d1d[e], d2d[e]);
+                            if (a_in) __stcs(o, v);
+                            o += pitch;
+                        }
+                    } else {
+#pragma unroll
+                        for (int hh = 0; hh < kBatch / 2; ++hh) {
+                            const float2 v = bilerp_fast2(make_float2(a00[2 * hh], a00[2 * hh + 1]),
+                                                          make_float2(a10[2 * hh], a10[2 * hh + 1]),
+                                                          make_float2(a01[2 * hh], a01[2 * hh + 1]),
+                                                          make_float2(a11[2 * hh], a11[2 * hh + 1]),
+                                                          d1p[hh], d2p[hh]);
+                            if (a_in) { __stcs(o, v.x); __stcs(o + pitch, v.y); }
+                            o += 2 * pitch;
+                        }
                     }
                 }
             }
@@ -297,24 +318,101 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact p
 struct Taps6 { uint32_t lo, hi; };   // bytes [o, o+4) and [o+4, o+8) of a byte stream
 
 template <typename LD>
-__device__ __forceinline__ Taps6 load6(const uint32_t* words, unsigned o, LD ld) {
+__device__ __forceinline__ Taps6 load6(const uint32_t* words, unsigned o, unsigned sel, LD ld) {
     const uint32_t* w = words + (o >> 2);
     const uint32_t w0 = ld(w), w1 = ld(w + 1), w2 = ld(w + 2);
-    const unsigned sel = 0x3210u + 0x1111u * (o & 3u);     // bytes sh..sh+3 of a register pair
     Taps6 t;
     t.lo = __byte_perm(w0, w1, sel);
     t.hi = __byte_perm(w1, w2, sel);
     return t;
 }
+__device__ __forceinline__ unsigned sel6(unsigned o) { return 0x3210u + 0x1111u * (o & 3u); }
 
-__device__ __forceinline__ float byte_f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+// byte k of w as a float without a conversion instruction: 0x4B000000 | b  ==  2^23 + b
+__device__ __forceinline__ float byte_f(uint32_t w, int k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + (unsigned)k)) - 8388608.0f;
+}
 __device__ __forceinline__ double byte_d(uint32_t w, int k) { return (double)((w >> (8 * k)) & 0xffu); }
+
+// t0 = source line i2, t1 = line i2+1;  t.lo = [a00.r a00.g a00.b a10.r], t.hi = [a10.g a10.b . .]
+template <bool EXACT>
+__device__ __forceinline__ uint32_t blend_rgb(const Taps6& t0, const Taps6& t1, double d1d, double d2d,
+                                              float d1f, float d2f) {
+    uint32_t r, g, b;
+    if (EXACT) {
+        r = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 0), byte_d(t0.lo, 3), byte_d(t1.lo, 0), byte_d(t1.lo, 3), d1d, d2d));
+        g = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 1), byte_d(t0.hi, 0), byte_d(t1.lo, 1), byte_d(t1.hi, 0), d1d, d2d));
+        b = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 2), byte_d(t0.hi, 1), byte_d(t1.lo, 2), byte_d(t1.hi, 1), d1d, d2d));
+    } else {
+        // round-to-nearest by magic add; weights in [0,1] keep the result inside [0,255]
+        const float m = 12582912.0f;
+        const float fr = bilerp_fast(byte_f(t0.lo, 0), byte_f(t0.lo, 3), byte_f(t1.lo, 0), byte_f(t1.lo, 3), d1f, d2f) + m;
+        const float fg = bilerp_fast(byte_f(t0.lo, 1), byte_f(t0.hi, 0), byte_f(t1.lo, 1), byte_f(t1.hi, 0), d1f, d2f) + m;
+        const float fb = bilerp_fast(byte_f(t0.lo, 2), byte_f(t0.hi, 1), byte_f(t1.lo, 2), byte_f(t1.hi, 1), d1f, d2f) + m;
+        r = __float_as_uint(fr); g = __float_as_uint(fg); b = __float_as_uint(fb);
+    }
+    // low bytes of r, g, b -> 0x00BBGGRR
+    return __byte_perm(__byte_perm(r, g, 0x0040), b, 0x0410);
+}
+
+__device__ __forceinline__ void store_rgb(uint8_t* q, uint32_t rgb) {
+    q[0] = (uint8_t)rgb; q[1] = (uint8_t)(rgb >> 8); q[2] = (uint8_t)(rgb >> 16);
+}
+
+// generic per-pixel path with every check and direct global taps
+template <bool EXACT>
+__device__ __forceinline__ uint32_t sample_direct_u8(const RectExact& pe, const RectFast& pf,
+                                                     const RowTermD& rtd, const RowTermF& rtf,
+                                                     const RectGeom& g, const uint8_t* __restrict__ sframe,
+                                                     unsigned pitch3, unsigned frame_bytes, int b,
+                                                     uint32_t fill) {
+    int g1, g2;
+    double d1d = 0, d2d = 0;
+    float d1f = 0, d2f = 0;
+    if (EXACT) {
+        double row, col;
+        rect_coord(pe, rtd, rect_q2(pe, g.axs1 + b), row, col);
+        if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) return fill;
+        lin_floor(row, g1, d1d);
+        lin_floor(col, g2, d2d);
+        lin_fix_edge(g.sz1, g1, d1d);
+        lin_fix_edge(g.sz2, g2, d2d);
+        g1 -= 1; g2 -= 1;
+    } else {
+        float row, col;
+        int t1, t2;
+        rect_coord(pf, rtf, (float)(g.axs1 + b) - pf.c2, row, col);
+        lin_floor_fast(row, t1, d1f);
+        lin_floor_fast(col, t2, d2f);
+        g1 = t1 - (kMagicBits + 1); g2 = t2 - (kMagicBits + 1);
+        if (!(((unsigned)g1 <= (unsigned)(g.sz1 - 2)) & ((unsigned)g2 <= (unsigned)(g.sz2 - 2)))) return fill;
+    }
+    const unsigned off = (unsigned)g2 * pitch3 + (unsigned)g1 * 3u;
+    Taps6 t0, t1;
+    // word-granular gather from a 4-byte aligned base; the byte path for the last few taps of
+    // the frame so nothing outside the caller's buffer is touched
+    if (off + pitch3 + 12u <= frame_bytes) {
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(sframe) & 3u);
+        const uint32_t* gwords = reinterpret_cast<const uint32_t*>(sframe - mis);
+        auto ld = [](const uint32_t* p) { return __ldg(p); };
+        t0 = load6(gwords, off + mis, sel6(off + mis), ld);
+        t1 = load6(gwords, off + pitch3 + mis, sel6(off + pitch3 + mis), ld);
+    } else {
+        const uint8_t* q = sframe + off;
+        t0.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+        t0.hi = q[4] | (q[5] << 8);
+        q += pitch3;
+        t1.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+        t1.hi = q[4] | (q[5] << 8);
+    }
+    return blend_rgb<EXACT>(t0, t1, d1d, d2d, d1f, d2f);
+}
 
 template <bool EXACT, bool TMA>
 __global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads)
 rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
                     const RectGeom g, const TileCfg cfg, const uint8_t* __restrict__ src,
-                    uint8_t* __restrict__ dst, uchar3 fill, unsigned frame_bytes) {
+                    uint8_t* __restrict__ dst, uchar3 fill3, unsigned frame_bytes) {
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemCtl ctl;
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -326,130 +424,122 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe
 
     if (TMA && warp == kWarps) {
         if (lane_id == 0) tma_prefetch_desc(&tmap);
-        for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
-            const int s = it % cfg.stages;
-            mbar_wait(&ctl.empty[s], ((it / cfg.stages) & 1) ^ 1);
+        int s = 0;
+        uint32_t phase = 1;
+        for (int tile = t_begin; tile < t_end; ++tile) {
+            mbar_wait(&ctl.empty[s], phase);
             producer_tile<EXACT, 3>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
                                     s, a_lo, tile, frame, lane_id);
+            if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
         return;
     }
 
     const int a = a_lo + lane_id;
+    const bool a_in = a < g.sz1;
+    const int a_c = min(a, g.sz1 - 1);
     const uint8_t* sframe = src + (long long)frame * g.frame_stride * 3;
-    uint8_t* ocol = dst + ((long long)frame * g.frame_stride + a) * 3;
     const unsigned pitch3 = (unsigned)g.pitch * 3u;
-    const unsigned box_pitch = (unsigned)cfg.box1 * 3u;           // bytes per box line (multiple of 16)
-    // word-granular global gather: 4-byte aligned base, and the byte path for the last
-    // few taps of the frame so nothing outside the caller's buffer is touched
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(sframe) & 3u);
-    const uint32_t* gwords = reinterpret_cast<const uint32_t*>(sframe - mis);
+    const unsigned box_pitch = (unsigned)cfg.box1 * 3u;           // bytes per box line (multiple of 48)
+    const uint32_t fill = fill3.x | (fill3.y << 8) | (fill3.z << 16);
     RowTermD rtd;
     RowTermF rtf;
-    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
-    auto ld_global = [](const uint32_t* p) { return __ldg(p); };
+    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
+    const int line0 = t_begin * kT + warp * kLines;
+    uint8_t* optr = dst + ((long long)frame * g.frame_stride + (long long)line0 * g.pitch + a) * 3;
+    float i2f = (float)(g.axs1 + line0) - pf.c2;
+    const long long tile_step = (long long)(kT - kLines) * g.pitch * 3;
     auto ld_shared = [](const uint32_t* p) { return *p; };
 
-    for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
-        const int s = it % cfg.stages;
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
         const int b0 = tile * kT + warp * kLines;
+        const bool full_lines = b0 + kLines <= g.sz2;
         int K1 = 0, R1 = 0, K2 = 0, R2 = 0;
         const uint32_t* box = nullptr;
         unsigned box_off = 0;
         const StageHdr* h = &ctl.hdr[s];
-        if (TMA) {
-            mbar_wait(&ctl.full[s], (it / cfg.stages) & 1);
-            K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
-            box = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)s * cfg.box_bytes);
-            box_off = (unsigned)h->base_off * 3u;   // base_off = lo2*box1 + lo1 (pixels)
-        }
 #pragma unroll
-        for (int e = 0; e < kLines; ++e) {
-            const int b = b0 + e;
-            if (b >= g.sz2) continue;
-            int i1, i2;
-            bool staged = false, have = false;
-            Taps6 t0, t1;
-            t0.lo = t0.hi = t1.lo = t1.hi = 0;
-            [[maybe_unused]] double rowd, cold, d1d, d2d;
-            [[maybe_unused]] float d1f, d2f;
-            if (EXACT) {
-                const double q2 = TMA ? h->q2[warp * kLines + e] : rect_q2(pe, g.axs1 + b);
-                rect_coord(pe, rtd, q2, rowd, cold);
-                lin_floor(rowd, i1, d1d);
-                lin_floor(cold, i2, d2d);
-            } else {
-                float row, col;
-                rect_coord(pf, rtf, (float)(g.axs1 + b) - pf.c2, row, col);
-                lin_floor_fast(row, i1, d1f);
-                lin_floor_fast(col, i2, d2f);
-            }
+        for (int batch = 0; batch < kLines / kBatch; ++batch) {
+            const int bb = b0 + batch * kBatch;
+            bool fast = false;
             if (TMA) {
-                const int l1 = i1 - K1, l2 = i2 - K2;
-                staged = ((unsigned)l1 < (unsigned)R1) & ((unsigned)l2 < (unsigned)R2);
+                int t1[kBatch], t2[kBatch];
+                bool guard = true;
+                [[maybe_unused]] double d1d[kBatch], d2d[kBatch];
+                [[maybe_unused]] float2 d1p[kBatch / 2], d2p[kBatch / 2];
                 if (EXACT) {
-                    const unsigned h1 = (unsigned)__double2hiint(rowd) - 0x3FF00000u;
-                    const unsigned h2 = (unsigned)__double2hiint(cold) - 0x3FF00000u;
-                    staged &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
-                }
-                if (staged) {
-                    const unsigned o = box_off + (unsigned)l2 * box_pitch + (unsigned)l1 * 3u;
-                    t0 = load6(box, o, ld_shared);
-                    t1 = load6(box, o + box_pitch, ld_shared);
-                    have = true;
-                }
-            }
-            if (!staged) {
-                bool ok;
-                int g1, g2;
-                if (EXACT) {
-                    ok = lin_ok(rowd, g.sz1) & lin_ok(cold, g.sz2);
-                    g1 = i1; g2 = i2;
-                    lin_fix_edge(g.sz1, g1, d1d);
-                    lin_fix_edge(g.sz2, g2, d2d);
-                    g1 -= 1; g2 -= 1;
-                } else {
-                    g1 = i1 - (kMagicBits + 1); g2 = i2 - (kMagicBits + 1);
-                    ok = ((unsigned)g1 <= (unsigned)(g.sz1 - 2)) & ((unsigned)g2 <= (unsigned)(g.sz2 - 2));
-                }
-                if (ok) {
-                    const unsigned off = (unsigned)g2 * pitch3 + (unsigned)g1 * 3u;
-                    if (off + pitch3 + 12u <= frame_bytes) {
-                        t0 = load6(gwords, off + mis, ld_global);
-                        t1 = load6(gwords, off + pitch3 + mis, ld_global);
-                    } else {                                   // last bytes of the frame
-                        const uint8_t* q = sframe + off;
-                        t0.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-                        t0.hi = q[4] | (q[5] << 8);
-                        q += pitch3;
-                        t1.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-                        t1.hi = q[4] | (q[5] << 8);
+                    if (batch == 0) mbar_wait(&ctl.full[s], phase);
+#pragma unroll
+                    for (int e = 0; e < kBatch; ++e) {
+                        double row, col;
+                        rect_coord(pe, rtd, h->q2[warp * kLines + batch * kBatch + e], row, col);
+                        lin_floor(row, t1[e], d1d[e]);
+                        lin_floor(col, t2[e], d2d[e]);
+                        const unsigned h1 = (unsigned)__double2hiint(row) - 0x3FF00000u;
+                        const unsigned h2 = (unsigned)__double2hiint(col) - 0x3FF00000u;
+                        guard &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
                     }
-                    have = true;
-                }
-            }
-            uint32_t r = fill.x, gg = fill.y, bb = fill.z;
-            if (have) {
-                // t.lo = [a00.r a00.g a00.b a10.r], t.hi = [a10.g a10.b . .]
-                if (EXACT) {
-                    r  = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 0), byte_d(t0.lo, 3), byte_d(t1.lo, 0), byte_d(t1.lo, 3), d1d, d2d));
-                    gg = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 1), byte_d(t0.hi, 0), byte_d(t1.lo, 1), byte_d(t1.hi, 0), d1d, d2d));
-                    bb = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 2), byte_d(t0.hi, 1), byte_d(t1.lo, 2), byte_d(t1.hi, 1), d1d, d2d));
                 } else {
-                    r  = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 0), byte_f(t0.lo, 3), byte_f(t1.lo, 0), byte_f(t1.lo, 3), d1f, d2f));
-                    gg = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 1), byte_f(t0.hi, 0), byte_f(t1.lo, 1), byte_f(t1.hi, 0), d1f, d2f));
-                    bb = (uint32_t)__float2int_rn(bilerp_fast(byte_f(t0.lo, 2), byte_f(t0.hi, 1), byte_f(t1.lo, 2), byte_f(t1.hi, 1), d1f, d2f));
-                    r = min(r, 255u); gg = min(gg, 255u); bb = min(bb, 255u);
+#pragma unroll
+                    for (int hh = 0; hh < kBatch / 2; ++hh) {
+                        float2 row, col;
+                        const float base = i2f + (float)(batch * kBatch + 2 * hh);
+                        rect_coord2(pf, rtf, make_float2(base, base + 1.0f), row, col);
+                        lin_floor_fast2(row, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
+                        lin_floor_fast2(col, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
+                    }
+                }
+                if (batch == 0) {
+                    if (!EXACT) mbar_wait(&ctl.full[s], phase);
+                    K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
+                    box = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)s * cfg.box_bytes);
+                    box_off = (unsigned)h->base_off * 3u;   // base_off = lo2*box1 + lo1 (pixels)
+                }
+                unsigned o[kBatch];
+                bool staged = guard;
+#pragma unroll
+                for (int e = 0; e < kBatch; ++e) {
+                    const int l1 = t1[e] - K1, l2 = t2[e] - K2;
+                    staged &= ((unsigned)l1 < (unsigned)R1) & ((unsigned)l2 < (unsigned)R2);
+                    o[e] = box_off + (unsigned)l2 * box_pitch + (unsigned)l1 * 3u;
+                }
+                fast = full_lines && __all_sync(0xffffffffu, staged);
+                if (fast) {
+                    uint8_t* q = optr;
+#pragma unroll
+                    for (int e = 0; e < kBatch; ++e) {
+                        const unsigned sel = sel6(o[e]);          // box_pitch % 4 == 0: same for both lines
+                        const Taps6 ta = load6(box, o[e], sel, ld_shared);
+                        const Taps6 tb = load6(box, o[e] + box_pitch, sel, ld_shared);
+                        uint32_t rgb;
+                        if (EXACT) rgb = blend_rgb<true>(ta, tb, d1d[e], d2d[e], 0.f, 0.f);
+                        else rgb = blend_rgb<false>(ta, tb, 0.0, 0.0, (e & 1) ? d1p[e / 2].y : d1p[e / 2].x,
+                                                    (e & 1) ? d2p[e / 2].y : d2p[e / 2].x);
+                        if (a_in) store_rgb(q, rgb);
+                        q += pitch3;
+                    }
                 }
             }
-            if (a < g.sz1) {
-                uint8_t* q = ocol + (long long)b * g.pitch * 3;
-                q[0] = (uint8_t)r; q[1] = (uint8_t)gg; q[2] = (uint8_t)bb;
+            if (!fast) {
+                uint8_t* q = optr;
+#pragma unroll
+                for (int e = 0; e < kBatch; ++e) {
+                    const int b = bb + e;
+                    if (b < g.sz2 && a_in)
+                        store_rgb(q, sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b, fill));
+                    q += pitch3;
+                }
             }
+            optr += (long long)kBatch * pitch3;
         }
+        i2f += (float)kT;
+        optr += tile_step;
         if (TMA) {
             __syncwarp();
             if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
+            if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
     }
 }

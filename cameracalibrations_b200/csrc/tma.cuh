@@ -30,10 +30,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(2000u) /* suspend-time hint, ns */ : "memory");
     return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
