@@ -25,6 +25,7 @@
 //  * Direct: the same kernel without the producer; taps come through L1/L2 (__ldg).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -37,6 +38,10 @@ constexpr int kT = 32;                 // tile edge
 constexpr int kWarps = 4;              // consumer warps per CTA
 constexpr int kLines = kT / kWarps;    // lines per warp per tile = pixels per thread per tile
 constexpr int kBatch = 4;              // lines whose taps are in flight together
+#ifndef CAMCAL_BATCH_EXACT
+#define CAMCAL_BATCH_EXACT 2
+#endif
+constexpr int kBatchExact = CAMCAL_BATCH_EXACT;   // FP64 values cost two registers each: smaller batches, more CTAs
 constexpr int kMaxStages = 4;
 constexpr int kConsumerThreads = 32 * kWarps;
 
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
                      const RectGeom g, const TileCfg cfg, const float* __restrict__ src,
                      float* __restrict__ dst, float fill) {
+    constexpr int kBatch = EXACT ? kBatchExact : 4;     // shadows the namespace constant
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemCtl ctl;
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -355,6 +361,26 @@ __device__ __forceinline__ uint32_t blend_rgb(const Taps6& t0, const Taps6& t1, 
     return __byte_perm(__byte_perm(r, g, 0x0040), b, 0x0410);
 }
 
+// two pixels at once (FADD2/FFMA2): same arithmetic as blend_rgb<false>
+__device__ __forceinline__ float2 byte_f2(uint32_t wp, uint32_t wq, int k) {
+    return add2(make_float2(__uint_as_float(__byte_perm(wp, 0x4B000000u, 0x7440u + (unsigned)k)),
+                            __uint_as_float(__byte_perm(wq, 0x4B000000u, 0x7440u + (unsigned)k))),
+                bc2(-8388608.0f));
+}
+__device__ __forceinline__ void blend_rgb2(const Taps6& p0, const Taps6& p1, const Taps6& q0,
+                                           const Taps6& q1, float2 d1, float2 d2, uint32_t& rgb_p,
+                                           uint32_t& rgb_q) {
+    const float2 m = bc2(12582912.0f);
+    const float2 fr = add2(bilerp_fast2(byte_f2(p0.lo, q0.lo, 0), byte_f2(p0.lo, q0.lo, 3),
+                                        byte_f2(p1.lo, q1.lo, 0), byte_f2(p1.lo, q1.lo, 3), d1, d2), m);
+    const float2 fg = add2(bilerp_fast2(byte_f2(p0.lo, q0.lo, 1), byte_f2(p0.hi, q0.hi, 0),
+                                        byte_f2(p1.lo, q1.lo, 1), byte_f2(p1.hi, q1.hi, 0), d1, d2), m);
+    const float2 fb = add2(bilerp_fast2(byte_f2(p0.lo, q0.lo, 2), byte_f2(p0.hi, q0.hi, 1),
+                                        byte_f2(p1.lo, q1.lo, 2), byte_f2(p1.hi, q1.hi, 1), d1, d2), m);
+    rgb_p = __byte_perm(__byte_perm(__float_as_uint(fr.x), __float_as_uint(fg.x), 0x0040), __float_as_uint(fb.x), 0x0410);
+    rgb_q = __byte_perm(__byte_perm(__float_as_uint(fr.y), __float_as_uint(fg.y), 0x0040), __float_as_uint(fb.y), 0x0410);
+}
+
 __device__ __forceinline__ void store_rgb(uint8_t* q, uint32_t rgb) {
     q[0] = (uint8_t)rgb; q[1] = (uint8_t)(rgb >> 8); q[2] = (uint8_t)(rgb >> 16);
 }
@@ -508,17 +534,29 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe
                 fast = full_lines && __all_sync(0xffffffffu, staged);
                 if (fast) {
                     uint8_t* q = optr;
+                    Taps6 ta[kBatch], tb[kBatch];
 #pragma unroll
                     for (int e = 0; e < kBatch; ++e) {
                         const unsigned sel = sel6(o[e]);          // box_pitch % 4 == 0: same for both lines
-                        const Taps6 ta = load6(box, o[e], sel, ld_shared);
-                        const Taps6 tb = load6(box, o[e] + box_pitch, sel, ld_shared);
-                        uint32_t rgb;
-                        if (EXACT) rgb = blend_rgb<true>(ta, tb, d1d[e], d2d[e], 0.f, 0.f);
-                        else rgb = blend_rgb<false>(ta, tb, 0.0, 0.0, (e & 1) ? d1p[e / 2].y : d1p[e / 2].x,
-                                                    (e & 1) ? d2p[e / 2].y : d2p[e / 2].x);
-                        if (a_in) store_rgb(q, rgb);
-                        q += pitch3;
+                        ta[e] = load6(box, o[e], sel, ld_shared);
+                        tb[e] = load6(box, o[e] + box_pitch, sel, ld_shared);
+                    }
+                    if (EXACT) {
+#pragma unroll
+                        for (int e = 0; e < kBatch; ++e) {
+                            const uint32_t rgb = blend_rgb<true>(ta[e], tb[e], d1d[e], d2d[e], 0.f, 0.f);
+                            if (a_in) store_rgb(q, rgb);
+                            q += pitch3;
+                        }
+                    } else {
+#pragma unroll
+                        for (int hh = 0; hh < kBatch / 2; ++hh) {
+                            uint32_t rgb0, rgb1;
+                            blend_rgb2(ta[2 * hh], tb[2 * hh], ta[2 * hh + 1], tb[2 * hh + 1], d1p[hh],
+                                       d2p[hh], rgb0, rgb1);
+                            if (a_in) { store_rgb(q, rgb0); store_rgb(q + pitch3, rgb1); }
+                            q += 2 * pitch3;
+                        }
                     }
                 }
             }
@@ -726,6 +764,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     const int box_bytes = box1 * pxb * box2;
     if (box_bytes > 40 * 1024) return false;     // footprint too large to be worth staging
     int stages = 3;
+    if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(2, atoi(e)));   // tuning knob
     while (stages > 2 && stages * box_bytes > 56 * 1024) --stages;
 
     cuuint64_t dims[3] = {(cuuint64_t)g.sz1 * (pxb == 4 ? 1 : 3), (cuuint64_t)g.sz2,
@@ -744,13 +783,15 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
 
 static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips) {
     cfg->ntiles2 = (g.sz2 + kT - 1) / kT;
-    // enough CTAs for ~6 waves of 4 CTAs/SM, but walks long enough to amortise the thread setup
-    const long long ctas_wanted = (long long)ctx->sm_count * 4 * 6;
+    // enough CTAs for ~12 waves of 4 CTAs/SM (tail effect: profiles/r1_rectify.md sweep), but
+    // walks long enough to amortise the thread setup
+    const long long ctas_wanted = (long long)ctx->sm_count * 4 * 12;
     const long long per_seg = (long long)strips * std::max(g.nframes, 1);
     long long segs = (ctas_wanted + per_seg - 1) / per_seg;
     if (segs < 1) segs = 1;
     int tps = (int)((cfg->ntiles2 + segs - 1) / segs);
     if (tps < 4) tps = std::min(4, cfg->ntiles2);
+    if (const char* e = getenv("CAMCAL_TPS")) tps = std::max(1, atoi(e));      // tuning knob
     cfg->tiles_per_seg = std::max(tps, 1);
 }
 

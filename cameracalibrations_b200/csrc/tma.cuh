@@ -30,14 +30,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(2000u) /* suspend-time hint, ns */ : "memory");
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
 }
+// Polling costs issue slots that other CTAs on the SM could use: back off between probes.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(256);
 }
 
 // 3-D tiled tensor load global -> shared, completion signalled on an mbarrier

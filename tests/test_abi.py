@@ -1,0 +1,101 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol that
+include/camcal_b200.h declares, fails loudly without a device, and the host-only helpers agree
+with the oracle.  No compute entry point is called here."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle_c as oc
+
+
+@pytest.fixture(scope="module")
+def cc():
+    import cameracalibrations_b200 as m
+    return m
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "camcal_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(cc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(cc):
+    from cameracalibrations_b200 import _lib
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/camcal_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTS)          # the ctypes table binds all of them
+    assert _lib.lib.cc_abi_version() == 1
+
+
+def test_no_cpu_fallback(cc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(cc.CamcalError) as e:
+        cc.Context(0)
+    assert e.value.status == -2                     # CC_ERR_NO_DEVICE
+    c = cc.Calibration((100.0, 100.0, 50.0, 50.0), [((0, 0, 0), (0, 0, 1.0))], 1.0, 0.0, ["extrinsic.png"])
+    with pytest.raises(cc.CamcalError):
+        c(np.zeros((4, 2)))                          # host entry point: still needs the GPU
+
+
+def test_argument_errors_are_status_codes(cc):
+    from cameracalibrations_b200 import _lib
+    out = C.c_double()
+    assert _lib.lib.cc_get_ratio(None, None, 5, 8, 1.0, C.byref(out)) == -1
+    assert b"NULL" in _lib.lib.cc_last_error_string()
+    assert _lib.lib.cc_ctx_create(0, None) == -1
+    n = C.c_uint64()
+    assert _lib.lib.cc_ctx_launch_count(None, C.byref(n)) == -1
+    assert _lib.lib.cc_ctx_destroy(None) == 0
+
+
+def test_get_ratio_get_axes_match_oracle(cc, example_fit):
+    n1, n2 = example_fit["n_corners"]
+    for vi in range(6):
+        ip = example_fit["corners_np"][vi].reshape(n2, n1, 2).transpose(1, 0, 2)
+        r = cc.get_ratio(ip, 1.0)
+        assert r == oc.get_ratio(ip, 1.0)
+        assert cc.get_axes(r, 1.0, (n1, n2), example_fit["sz"]) == oc.get_axes(r, 1.0, (n1, n2), example_fit["sz"])
+    ip = example_fit["corners_np"][0].reshape(n2, n1, 2).transpose(1, 0, 2)
+    assert cc.get_axes(cc.get_ratio(ip, 1.0), 1.0, (n1, n2), (375, 500)) == (-112, -119)
+
+
+def test_calibration_object_and_json_round_trip(cc, tmp_path, example_fit):
+    """test/runtests.jl:88-98: save -> load preserves files (and here also the numbers)."""
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        org = cc.Calibration(rng.random(4), [(rng.random(3), rng.random(3)) for _ in range(5)],
+                             rng.random(), rng.random(), ["".join(rng.choice(list("abcdefgh"), 5)) for _ in range(5)])
+        f = tmp_path / "calibration.json"
+        cc.save(f, org)
+        copy = cc.load(f)
+        assert org.files == copy.files
+        assert org.intrinsic == copy.intrinsic and org.extrinsics == copy.extrinsics
+        assert org.scale == copy.scale and org.k == copy.k
+    d = json.load(open(f))
+    assert set(d) == {"intrinsic", "extrinsics", "scale", "k", "files"}      # CalibrationIO, src/io.jl:9-15
+    # a rotation stored as a 3x3 matrix (column-major) loads to the same rotation vector
+    from oracle import oracle_np as on
+    rv = np.array([0.3, -0.2, 0.5])
+    d["extrinsics"][0]["linear"] = on.rodrigues(rv).T.ravel().tolist()
+    json.dump(d, open(f, "w"))
+    np.testing.assert_allclose(cc.load(f).extrinsics[0][0], rv, atol=1e-12)
+
+
+def test_view_index_semantics(cc):
+    c = cc.Calibration((1.0, 1.0, 0.0, 0.0), [((0, 0, 0), (0, 0, 1.0))] * 3, 1.0, 0.0, ["a.png", "x_extrinsic_1.png", "b.png"])
+    assert c._index(None) == 1 and c._index("b.png") == 2 and c._index(0) == 0
+    with pytest.raises(IndexError):
+        c._index(3)
+    with pytest.raises(ValueError):
+        c._index("missing.png")
+    assert c.checker_size == 1.0
