@@ -1,0 +1,149 @@
+# CameraCalibrationsB200.jl -- the `ccall` shim a maintainer of CameraCalibrations.jl adds to
+# evaluate a fitted `Calibration` on a B200 through libcamcal_b200.so (include/camcal_b200.h).
+#
+# NOT RUN IN THIS REPOSITORY'S CI: the build image has no Julia (SURVEY.md F1).  The Python
+# package `cameracalibrations_b200` binds the very same symbols with ctypes and is what the tests
+# and bench.py exercise; this file is the reference-side binding shown in INTEGRATION.md.
+#
+# Nothing of the reference's API changes: `fit`, `Calibration`, `save`/`load`, the scalar
+# callables `c(::RowCol, i)` / `c(::XYZ, i)` and `rectification` stay as they are
+# (src/meta.jl:82-103).  This module ADDS batch methods that take whole arrays and run on the GPU.
+module CameraCalibrationsB200
+
+using CameraCalibrations: Calibration, RowCol, XYZ
+using StaticArrays
+
+const libcamcal = get(ENV, "LIBCAMCAL_B200", "libcamcal_b200.so")
+
+# ---- PODs of include/camcal_b200.h ------------------------------------------------------------
+struct CcIntr            # cc_intr
+    frow::Cdouble; fcol::Cdouble; crow::Cdouble; ccol::Cdouble; k::Cdouble; checker_size::Cdouble
+end
+struct CcView            # cc_view
+    rvec::NTuple{3,Cdouble}; tvec::NTuple{3,Cdouble}
+end
+
+# Calibration fields -> PODs (src/meta.jl:17-25, src/buildcalibrations.jl:1-6)
+function CcIntr(c::Calibration)
+    d = c.intrinsic.linear.diag
+    t = c.intrinsic.translation
+    CcIntr(d[1], d[2], t[1], t[2], c.k, 1 / c.scale.linear.diag[1])
+end
+function CcView(c::Calibration, i::Int)
+    e = c.extrinsics[i]                      # AffineMap{RotationVec, SVector{3}}
+    r = e.linear
+    CcView((r.sx, r.sy, r.sz), Tuple(e.translation))
+end
+
+struct CamcalError <: Exception
+    status::Cint
+    msg::String
+end
+function check(rc::Cint)
+    rc == 0 && return nothing
+    throw(CamcalError(rc, unsafe_string(ccall((:cc_last_error_string, libcamcal), Cstring, ()))))
+end
+
+# ---- context ------------------------------------------------------------------------------------
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:cc_ctx_create, libcamcal), Cint, (Cint, Ptr{Ptr{Cvoid}}), device, h))
+        ctx = new(h[])
+        finalizer(x -> ccall((:cc_ctx_destroy, libcamcal), Cint, (Ptr{Cvoid},), x.handle), ctx)
+        ctx
+    end
+end
+const CTX = Ref{Union{Nothing,Context}}(nothing)
+context() = something(CTX[], (CTX[] = Context(0)))
+
+# ---- batch pixel -> world: bulk form of c.(imgpoints, i), src/buildcalibrations.jl:46 --------
+"""
+    c(rows::Vector{Float64}, cols::Vector{Float64}, i) -> (x, y, z)
+
+SoA batch of `(c::Calibration)(::RowCol, i)` (src/meta.jl:82) on the GPU (host arrays in and out).
+"""
+function (c::Calibration)(rows::Vector{Float64}, cols::Vector{Float64}, i::Int)
+    n = length(rows); @assert length(cols) == n
+    checkbounds(c.extrinsics, i)             # BoundsError like the reference
+    x, y, z = similar(rows), similar(rows), similar(rows)
+    intr, view = Ref(CcIntr(c)), Ref(CcView(c, i))
+    check(ccall((:cc_img2world_f64_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Ref{CcView}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cdouble}, Csize_t),
+                context().handle, intr, view, rows, cols, x, y, z, n))
+    x, y, z
+end
+
+"Batch of `rectification(c, i)` (src/meta.jl:99): z is not computed."
+function rectification_batch(c::Calibration, i::Int, rows::Vector{Float64}, cols::Vector{Float64})
+    n = length(rows)
+    x, y = similar(rows), similar(rows)
+    check(ccall((:cc_img2world_f64_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Ref{CcView}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cdouble}, Csize_t),
+                context().handle, Ref(CcIntr(c)), Ref(CcView(c, i)), rows, cols, x, y, C_NULL, n))
+    x, y
+end
+
+# ---- batch world -> pixel: bulk form of c.(objpoints, i), src/buildcalibrations.jl:29 --------
+function (c::Calibration)(x::Vector{Float64}, y::Vector{Float64}, z::Vector{Float64}, i::Int)
+    n = length(x)
+    checkbounds(c.extrinsics, i)
+    rows, cols = similar(x), similar(x)
+    check(ccall((:cc_world2img_f64_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Ref{CcView}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Cdouble}, Csize_t),
+                context().handle, Ref(CcIntr(c)), Ref(CcView(c, i)), x, y, z, rows, cols, n))
+    rows, cols
+end
+
+# ---- full-frame rectification: warp(img, tform, axs), src/plot_calibration.jl:40 -------------
+# `imgs` is a stack of frames of size (sz1, sz2, nframes): the memory is passed as is (first
+# RowCol axis contiguous).  `ratio` from get_ratio (:8-13), `axs` from get_axes (:1-6).
+function warp_batch(c::Calibration, i::Int, imgs::Array{Float32,3}, ratio::Float64,
+                    axs::NTuple{2,<:AbstractUnitRange}; fill::Float32 = NaN32, fast::Bool = false)
+    sz1, sz2, nf = size(imgs)
+    out = similar(imgs)
+    axs_min = Int64[first(axs[1]), first(axs[2])]
+    check(ccall((:cc_rectify_f32c1_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Ref{CcView}, Cdouble, Ptr{Int64}, Ptr{Cfloat}, Ptr{Cfloat},
+                 Cint, Cint, Csize_t, Csize_t, Cint, Cfloat, Cuint),
+                context().handle, Ref(CcIntr(c)), Ref(CcView(c, i)), ratio, axs_min, imgs, out,
+                sz1, sz2, sz1, sz1 * sz2, nf, fill, fast ? 1 : 0))
+    out
+end
+
+# RGB{N0f8} frames: reinterpret(UInt8, imgs) has size (3, sz1, sz2, nframes) = u8c3 layout
+function warp_batch(c::Calibration, i::Int, imgs::Array{UInt8,4}, ratio::Float64,
+                    axs::NTuple{2,<:AbstractUnitRange}; fill::NTuple{3,UInt8} = (0x00, 0x00, 0x00),
+                    fast::Bool = false)
+    @assert size(imgs, 1) == 3
+    _, sz1, sz2, nf = size(imgs)
+    out = similar(imgs)
+    axs_min = Int64[first(axs[1]), first(axs[2])]
+    check(ccall((:cc_rectify_u8c3_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Ref{CcView}, Cdouble, Ptr{Int64}, Ptr{UInt8}, Ptr{UInt8},
+                 Cint, Cint, Csize_t, Csize_t, Cint, Ptr{UInt8}, Cuint),
+                context().handle, Ref(CcIntr(c)), Ref(CcView(c, i)), ratio, axs_min, imgs, out,
+                sz1, sz2, sz1, sz1 * sz2, nf, UInt8[fill...], fast ? 1 : 0))
+    out
+end
+
+# ---- residual + normal-equation blocks (what calibrateCamera reduces, src/detect_fit.jl:47) ---
+function reproj_jtj(c::Calibration, aspect::Float64, objpoints::Matrix{Float64},   # 3 x ncorners
+                    imgpoints::Array{Float64,3})                                    # 2 x ncorners x nviews
+    nc, nv = size(imgpoints, 2), size(imgpoints, 3)
+    views = [CcView(c, i) for i in 1:nv]
+    per_view = Matrix{Float64}(undef, 66, nv)
+    shared = Vector{Float64}(undef, 21)
+    check(ccall((:cc_reproj_jtj_f64_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Cdouble, Ptr{CcView}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint,
+                 Ptr{Cdouble}, Ptr{Cdouble}),
+                context().handle, Ref(CcIntr(c)), aspect, views, nv, objpoints, imgpoints, nc,
+                per_view, shared))
+    per_view, shared
+end
+
+end # module
