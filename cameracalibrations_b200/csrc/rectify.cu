@@ -42,6 +42,18 @@ constexpr int kBatch = 4;              // lines whose taps are in flight togethe
 #define CAMCAL_BATCH_EXACT 2
 #endif
 constexpr int kBatchExact = CAMCAL_BATCH_EXACT;   // FP64 values cost two registers each: smaller batches, more CTAs
+#ifndef CAMCAL_BATCH_FAST
+#define CAMCAL_BATCH_FAST 4
+#endif
+constexpr int kBatchFast = CAMCAL_BATCH_FAST;
+// floor of the exact path, per axis: 0 = FRND.F64.FLOOR (XU pipe), 1 = DADD.RM (FP64 pipe)
+#ifndef CAMCAL_FLOOR1
+#define CAMCAL_FLOOR1 0
+#endif
+#ifndef CAMCAL_FLOOR2
+#define CAMCAL_FLOOR2 1
+#endif
+constexpr int kFloorMode1 = CAMCAL_FLOOR1, kFloorMode2 = CAMCAL_FLOOR2;
 constexpr int kMaxStages = 4;
 constexpr int kConsumerThreads = 32 * kWarps;
 
@@ -58,7 +70,10 @@ struct __align__(16) StageHdr {
     int x0, y0;            // box origin (0-based texel indices; may be negative)
     int K1, R1, K2, R2;    // fused index / range constants (see consumer)
     int base_off;          // pixel offset of (lo1, lo2) inside the box
-    int pad;
+    uint32_t base;         // shared-memory byte address of local tap (0, 0) (f32c1)
+    double Mk1, Mk2;       // exact: 2^52 - K   (K = global 1-based index of local tap 0)
+    float mk1, mk2;        // fast:  1.5*2^23 - K
+    int pad[2];
     double q2[kT];         // exact path: second-axis world term of every line of the tile
 };
 
@@ -110,6 +125,12 @@ __device__ __forceinline__ void producer_tile(const CUtensorMap* tmap, const Rec
         h->R1 = max(0, hi1 - lo1 + 1);
         h->R2 = max(0, hi2 - lo2 + 1);
         h->base_off = lo2 * cfg.box1 + lo1;
+        const int k1 = 1 + x0 + lo1, k2 = 1 + y0 + lo2;
+        h->Mk1 = 4503599627370496.0 - (double)k1;
+        h->Mk2 = 4503599627370496.0 - (double)k2;
+        h->mk1 = 12582912.0f - (float)k1;
+        h->mk2 = 12582912.0f - (float)k2;
+        h->base = smem_u32(stage) + (uint32_t)(lo2 * cfg.box1 + lo1) * (PXB == 1 ? 4u : 3u);
     }
     __syncwarp();
     if (lane_id == 0) {
@@ -129,192 +150,9 @@ __device__ __forceinline__ void pipeline_init(SmemCtl* ctl, int stages, bool tma
     if (tma) __syncthreads();
 }
 
-// --------------------------------------------------------------------------------------
-// fp32 single channel
-// --------------------------------------------------------------------------------------
-// generic per-pixel path: every check, direct global taps.  Used by the direct variant and,
-// in the staged variant, by the (border) warps whose taps are not all inside the staged box.
-template <bool EXACT>
-__device__ __forceinline__ float sample_direct_f32(const RectExact& pe, const RectFast& pf,
-                                                   const RowTermD& rtd, const RowTermF& rtf,
-                                                   const RectGeom& g, const float* __restrict__ sframe,
-                                                   unsigned pitch, int b, float fill) {
-    if (EXACT) {
-        double row, col, d1, d2;
-        int i1, i2;
-        rect_coord(pe, rtd, rect_q2(pe, g.axs1 + b), row, col);
-        if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) return fill;
-        lin_floor(row, i1, d1);
-        lin_floor(col, i2, d2);
-        lin_fix_edge(g.sz1, i1, d1);
-        lin_fix_edge(g.sz2, i2, d2);
-        const float* q = sframe + ((unsigned)(i2 - 1) * pitch + (unsigned)(i1 - 1));
-        return (float)bilerp((double)__ldg(q), (double)__ldg(q + 1), (double)__ldg(q + pitch),
-                             (double)__ldg(q + pitch + 1), d1, d2);
-    } else {
-        float row, col, d1, d2;
-        int t1, t2;
-        rect_coord(pf, rtf, (float)(g.axs1 + b) - pf.c2, row, col);
-        lin_floor_fast(row, t1, d1);
-        lin_floor_fast(col, t2, d2);
-        const int g1 = t1 - (kMagicBits + 1), g2 = t2 - (kMagicBits + 1);
-        if (!(((unsigned)g1 <= (unsigned)(g.sz1 - 2)) & ((unsigned)g2 <= (unsigned)(g.sz2 - 2)))) return fill;
-        const float* q = sframe + ((unsigned)g2 * pitch + (unsigned)g1);
-        return bilerp_fast(__ldg(q), __ldg(q + 1), __ldg(q + pitch), __ldg(q + pitch + 1), d1, d2);
-    }
-}
-
-template <bool EXACT, bool TMA>
-__global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads)
-rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
-                     const RectGeom g, const TileCfg cfg, const float* __restrict__ src,
-                     float* __restrict__ dst, float fill) {
-    constexpr int kBatch = EXACT ? kBatchExact : 4;     // shadows the namespace constant
-    extern __shared__ __align__(128) uint8_t stage_mem[];
-    __shared__ SmemCtl ctl;
-    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int a_lo = blockIdx.x * kT;
-    const int frame = blockIdx.z;
-    const int t_begin = blockIdx.y * cfg.tiles_per_seg;
-    const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
-    pipeline_init(&ctl, cfg.stages, TMA);
-
-    if (TMA && warp == kWarps) {                       // ---- producer warp
-        if (lane_id == 0) tma_prefetch_desc(&tmap);
-        int s = 0;
-        uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
-        for (int tile = t_begin; tile < t_end; ++tile) {
-            mbar_wait(&ctl.empty[s], phase);
-            producer_tile<EXACT, 1>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
-                                    s, a_lo, tile, frame, lane_id);
-            if (++s == cfg.stages) { s = 0; phase ^= 1; }
-        }
-        return;
-    }
-
-    // ---- consumer warps
-    const int a = a_lo + lane_id;
-    const bool a_in = a < g.sz1;
-    const float* sframe = src + (long long)frame * g.frame_stride;
-    const unsigned pitch = (unsigned)g.pitch;
-    const int box1 = cfg.box1;
-    RowTermD rtd;
-    RowTermF rtf;
-    const int a_c = min(a, g.sz1 - 1);                 // out-of-frame lanes shadow the last pixel
-    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-    const int line0 = t_begin * kT + warp * kLines;
-    float* optr = dst + (long long)frame * g.frame_stride + (long long)line0 * g.pitch + a;
-    float i2f = (float)(g.axs1 + line0) - pf.c2;       // fast path: second-axis index, advanced per line
-    const long long tile_step = (long long)(kT - kLines) * g.pitch;
-
-    int s = 0;
-    uint32_t phase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const int b0 = tile * kT + warp * kLines;
-        const bool full_lines = b0 + kLines <= g.sz2;
-        int K1 = 0, R1 = 0, K2 = 0, R2 = 0;
-        const float* box = nullptr;
-        const StageHdr* h = &ctl.hdr[s];
-#pragma unroll
-        for (int batch = 0; batch < kLines / kBatch; ++batch) {
-            const int bb = b0 + batch * kBatch;
-            bool fast = false;
-            if (TMA) {
-                // coordinates first: they do not depend on the staged box, so the TMA
-                // latency of this tile hides behind them
-                int t1[kBatch], t2[kBatch];
-                bool guard = true;
-                [[maybe_unused]] double d1d[kBatch], d2d[kBatch];
-                [[maybe_unused]] float2 d1p[kBatch / 2], d2p[kBatch / 2];
-                if (EXACT) {
-                    if (batch == 0) mbar_wait(&ctl.full[s], phase);   // q2 comes from the header
-#pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        double row, col;
-                        rect_coord(pe, rtd, h->q2[warp * kLines + batch * kBatch + e], row, col);
-                        lin_floor(row, t1[e], d1d[e]);
-                        lin_floor(col, t2[e], d2d[e]);
-                        // lin_floor is only meaningful for 1 <= x < 2^31
-                        const unsigned h1 = (unsigned)__double2hiint(row) - 0x3FF00000u;
-                        const unsigned h2 = (unsigned)__double2hiint(col) - 0x3FF00000u;
-                        guard &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
-                    }
-                } else {
-#pragma unroll
-                    for (int hh = 0; hh < kBatch / 2; ++hh) {
-                        float2 row, col;
-                        const float base = i2f + (float)(batch * kBatch + 2 * hh);
-                        rect_coord2(pf, rtf, make_float2(base, base + 1.0f), row, col);
-                        lin_floor_fast2(row, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
-                        lin_floor_fast2(col, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
-                    }
-                }
-                if (batch == 0) {
-                    if (!EXACT) mbar_wait(&ctl.full[s], phase);
-                    K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
-                    box = reinterpret_cast<const float*>(stage_mem + (size_t)s * cfg.box_bytes) + h->base_off;
-                }
-                int l1[kBatch], l2[kBatch];
-                bool staged = guard;
-#pragma unroll
-                for (int e = 0; e < kBatch; ++e) {
-                    l1[e] = t1[e] - K1;
-                    l2[e] = t2[e] - K2;
-                    staged &= ((unsigned)l1[e] < (unsigned)R1) & ((unsigned)l2[e] < (unsigned)R2);
-                }
-                fast = full_lines && __all_sync(0xffffffffu, staged);
-                if (fast) {
-                    float a00[kBatch], a10[kBatch], a01[kBatch], a11[kBatch];
-#pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        const float* q = box + (l2[e] * box1 + l1[e]);
-                        a00[e] = q[0]; a10[e] = q[1];
-                        a01[e] = q[box1]; a11[e] = q[box1 + 1];
-                    }
-                    float* o = optr;
-                    if (EXACT) {
-#pragma unroll
-                        for (int e = 0; e < kBatch; ++e) {
-                            const float v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
-                                                          (double)a11[e], d1d[e], d2d[e]);
-                            if (a_in) __stcs(o, v);
-                            o += pitch;
-                        }
-                    } else {
-#pragma unroll
-                        for (int hh = 0; hh < kBatch / 2; ++hh) {
-                            const float2 v = bilerp_fast2(make_float2(a00[2 * hh], a00[2 * hh + 1]),
-                                                          make_float2(a10[2 * hh], a10[2 * hh + 1]),
-                                                          make_float2(a01[2 * hh], a01[2 * hh + 1]),
-                                                          make_float2(a11[2 * hh], a11[2 * hh + 1]),
-                                                          d1p[hh], d2p[hh]);
-                            if (a_in) { __stcs(o, v.x); __stcs(o + pitch, v.y); }
-                            o += 2 * pitch;
-                        }
-                    }
-                }
-            }
-            if (!fast) {
-                float* o = optr;
-#pragma unroll
-                for (int e = 0; e < kBatch; ++e) {
-                    const int b = bb + e;
-                    if (b < g.sz2 && a_in)
-                        __stcs(o, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b, fill));
-                    o += pitch;
-                }
-            }
-            optr += (long long)kBatch * pitch;
-        }
-        i2f += (float)kT;
-        optr += tile_step;
-        if (TMA) {
-            __syncwarp();
-            if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
-            if (++s == cfg.stages) { s = 0; phase ^= 1; }
-        }
-    }
-}
+}  // namespace cc
+#include "rectify_f32c1.cuh"
+namespace cc {
 
 // --------------------------------------------------------------------------------------
 // u8 x 3 interleaved (RGB{N0f8}).  Each tap is 3 bytes at byte offset 3*i; the two taps of
