@@ -25,6 +25,7 @@
 //  * Direct: the same kernel without the producer; taps come through L1/L2 (__ldg).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -34,10 +35,15 @@
 
 namespace cc {
 
-constexpr int kT = 32;                 // tile edge
+constexpr int kT = 32;                 // strip width along the first axis = lanes of a warp
 constexpr int kWarps = 4;              // consumer warps per CTA
-constexpr int kLines = kT / kWarps;    // lines per warp per tile = pixels per thread per tile
-constexpr int kBatch = 4;              // lines whose taps are in flight together
+constexpr int kLines = kT / kWarps;    // u8c3: lines per warp per (32-line) tile
+constexpr int kBatch = 4;              // u8c3: lines whose taps are in flight together
+#ifndef CAMCAL_TL_F32
+#define CAMCAL_TL_F32 64
+#endif
+constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTLf / kWarps of them)
+constexpr int kTLmax = 64;
 #ifndef CAMCAL_BATCH_EXACT
 #define CAMCAL_BATCH_EXACT 2
 #endif
@@ -67,14 +73,13 @@ struct TileCfg {
 
 // per-stage header written by the producer warp
 struct __align__(16) StageHdr {
-    int x0, y0;            // box origin (0-based texel indices; may be negative)
-    int K1, R1, K2, R2;    // fused index / range constants (see consumer)
-    int base_off;          // pixel offset of (lo1, lo2) inside the box
-    uint32_t base;         // shared-memory byte address of local tap (0, 0) (f32c1)
     double Mk1, Mk2;       // exact: 2^52 - K   (K = global 1-based index of local tap 0)
     float mk1, mk2;        // fast:  1.5*2^23 - K
-    int pad[2];
-    double q2[kT];         // exact path: second-axis world term of every line of the tile
+    uint32_t R1, R2;       // number of valid local first-tap indices per axis (0: nothing staged)
+    uint32_t base;         // shared-memory byte address of local tap (0, 0) (f32c1)
+    int K1, K2;            // u8c3: fused index constants (see consumer)
+    int base_off;          // u8c3: pixel offset of (lo1, lo2) inside the box
+    double q2[kTLmax];     // exact path: second-axis world term of every line of the tile
 };
 
 struct SmemCtl {
@@ -84,17 +89,33 @@ struct SmemCtl {
 };
 
 // --------------------------------------------------------------------------------------
-// producer: box origin from the four tile corners (FP32 map, even for the exact kernels --
-// it only positions the box), header, TMA issue.  PXB = 1 (f32c1 elements) or 3 (u8c3 bytes).
+// producer: box origin from 32 samples on the tile perimeter (FP32 map, even for the exact
+// kernels -- it only positions the box), header, TMA issue.
+// PXB = 1 (f32c1 elements) or 3 (u8c3 bytes); TL = lines per tile.
 // --------------------------------------------------------------------------------------
-template <bool EXACT, int PXB>
+__device__ __forceinline__ void perimeter_sample(int lane_id, int a_lo, int a_hi, int b_lo, int b_hi,
+                                                 int& ca, int& cb) {
+    // lanes 0-15: the two edges a = a_lo / a_hi, 8 samples each; lanes 16-31: b = b_lo / b_hi
+    const int j = lane_id & 7;
+    const bool far = (lane_id & 8) != 0;
+    if (lane_id < 16) {
+        ca = far ? a_hi : a_lo;
+        cb = b_lo + ((b_hi - b_lo) * j) / 7;
+    } else {
+        cb = far ? b_hi : b_lo;
+        ca = a_lo + ((a_hi - a_lo) * j) / 7;
+    }
+}
+
+template <bool EXACT, int PXB, int TL>
 __device__ __forceinline__ void producer_tile(const CUtensorMap* tmap, const RectFast& pf,
                                               const RectExact& pe, const RectGeom& g,
                                               const TileCfg& cfg, SmemCtl* ctl, uint8_t* stage,
                                               int s, int a_lo, int tile, int frame, int lane_id) {
-    const int b_lo = tile * kT;
-    const int a_hi = min(a_lo + kT - 1, g.sz1 - 1), b_hi = min(b_lo + kT - 1, g.sz2 - 1);
-    const int ca = (lane_id & 1) ? a_hi : a_lo, cb = (lane_id & 2) ? b_hi : b_lo;   // lanes 0..3: corners
+    const int b_lo = tile * TL;
+    const int a_hi = min(a_lo + kT - 1, g.sz1 - 1), b_hi = min(b_lo + TL - 1, g.sz2 - 1);
+    int ca, cb;
+    perimeter_sample(lane_id, a_lo, a_hi, b_lo, b_hi, ca, cb);
     const RowTermF rt = rect_row_term(pf, g.axs0 + ca);
     float row, col;
     rect_coord(pf, rt, (float)(g.axs1 + cb) - pf.c2, row, col);
@@ -103,27 +124,38 @@ __device__ __forceinline__ void producer_tile(const CUtensorMap* tmap, const Rec
     col = fminf(fmaxf(col, -4.0f), (float)g.sz2 + 4.0f);
     int r0 = (row == row) ? (int)floorf(row) : -4;
     int c0 = (col == col) ? (int)floorf(col) : -4;
-    r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, 1));
-    r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, 2));
-    c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, 1));
-    c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    r0 = __reduce_min_sync(0xffffffffu, r0);
+    c0 = __reduce_min_sync(0xffffffffu, c0);
+    // the branch-free reciprocal of the exact consumers needs a sane exponent: P3 is monotone in
+    // each output index, so the four corners bound it over the tile (same FP64 formula)
+    bool p3_ok = true;
+    if (EXACT) {
+        const int ka = (lane_id & 1) ? a_hi : a_lo, kb = (lane_id & 2) ? b_hi : b_lo;
+        const RowTermD rd = rect_row_term(pe, g.axs0 + ka);
+        const double P3 = fma(pe.R1[2], rect_q2(pe, g.axs1 + kb), rd.B3);
+        const bool sane = fabs(P3) >= 1e-270 && fabs(P3) <= 1e270;
+        p3_ok = __all_sync(0xffffffffu, sane) &&
+                (__all_sync(0xffffffffu, P3 > 0.0) || __all_sync(0xffffffffu, P3 < 0.0));
+    }
     // first tap index is floor - 1 (0-based); one texel of slack for the FP32 estimate.
     // The first-axis origin is rounded down so that the byte address stays 16-byte aligned.
-    int x0 = __shfl_sync(0xffffffffu, r0, 0) - 2;
-    const int y0 = __shfl_sync(0xffffffffu, c0, 0) - 2;
+    int x0 = r0 - 2;
+    const int y0 = c0 - 2;
     constexpr int kAlign = (PXB == 1) ? 4 : 16;
     x0 = (x0 >= 0) ? (x0 / kAlign) * kAlign : -(((-x0) + kAlign - 1) / kAlign) * kAlign;
     StageHdr* h = &ctl->hdr[s];
-    if (EXACT) h->q2[lane_id] = rect_q2(pe, g.axs1 + b_lo + lane_id);
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < TL / 32; ++i) h->q2[lane_id + 32 * i] = rect_q2(pe, g.axs1 + b_lo + lane_id + 32 * i);
+    }
     if (lane_id == 0) {
         // valid local range of the first tap: inside the box (both taps) and inside the frame
         const int lo1 = max(0, -x0), hi1 = min(cfg.box1 - 2, g.sz1 - 2 - x0);
         const int lo2 = max(0, -y0), hi2 = min(cfg.box2 - 2, g.sz2 - 2 - y0);
-        h->x0 = x0; h->y0 = y0;
         h->K1 = (EXACT ? 1 : kMagicBits + 1) + x0 + lo1;
         h->K2 = (EXACT ? 1 : kMagicBits + 1) + y0 + lo2;
-        h->R1 = max(0, hi1 - lo1 + 1);
-        h->R2 = max(0, hi2 - lo2 + 1);
+        h->R1 = p3_ok ? (uint32_t)max(0, hi1 - lo1 + 1) : 0u;
+        h->R2 = (uint32_t)max(0, hi2 - lo2 + 1);
         h->base_off = lo2 * cfg.box1 + lo1;
         const int k1 = 1 + x0 + lo1, k2 = 1 + y0 + lo2;
         h->Mk1 = 4503599627370496.0 - (double)k1;
@@ -292,7 +324,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe
         uint32_t phase = 1;
         for (int tile = t_begin; tile < t_end; ++tile) {
             mbar_wait(&ctl.empty[s], phase);
-            producer_tile<EXACT, 3>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
+            producer_tile<EXACT, 3, kT>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
                                     s, a_lo, tile, frame, lane_id);
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
@@ -357,7 +389,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe
                 }
                 if (batch == 0) {
                     if (!EXACT) mbar_wait(&ctl.full[s], phase);
-                    K1 = h->K1; R1 = h->R1; K2 = h->K2; R2 = h->R2;
+                    K1 = h->K1; R1 = (int)h->R1; K2 = h->K2; R2 = (int)h->R2;
                     box = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)s * cfg.box_bytes);
                     box_off = (unsigned)h->base_off * 3u;   // base_off = lo2*box1 + lo1 (pixels)
                 }
@@ -514,31 +546,35 @@ static void host_coord(const ChainD& ch, double inv_ratio, long long I1, long lo
 // Largest source footprint of any 32x32 output tile that touches the frame, from the tile
 // corners (the kernel positions each box from the same four corners).  Cached: a video
 // stream calls with the same calibration over and over.
-struct PlanKey { ChainD ch; double ratio; RectGeom g; };
+struct PlanKey { ChainD ch; double ratio; RectGeom g; int tl; };
 struct Plan { PlanKey key; bool valid; int need1, need2; };
 static Plan g_plan_cache[8];
 static int g_plan_next = 0;
 static std::mutex g_plan_mutex;
 
-static void footprint(const ChainD& ch, double ratio, const RectGeom& g, int* need1, int* need2) {
+static void footprint(const ChainD& ch, double ratio, const RectGeom& g, int tl, int* need1, int* need2) {
     const double inv_ratio = 1.0 / ratio;
-    const int n1 = (g.sz1 + kT - 1) / kT, n2 = (g.sz2 + kT - 1) / kT;
+    const int n1 = (g.sz1 + kT - 1) / kT, n2 = (g.sz2 + tl - 1) / tl;
     int m1 = 0, m2 = 0;
     for (int t2 = 0; t2 < n2; ++t2) {
-        const int b_lo = t2 * kT, b_hi = std::min(b_lo + kT - 1, g.sz2 - 1);
+        const int b_lo = t2 * tl, b_hi = std::min(b_lo + tl - 1, g.sz2 - 1);
         for (int t1 = 0; t1 < n1; ++t1) {
             const int a_lo = t1 * kT, a_hi = std::min(a_lo + kT - 1, g.sz1 - 1);
-            double r[4], c[4];
-            host_coord(ch, inv_ratio, g.axs0 + a_lo, g.axs1 + b_lo, &r[0], &c[0]);
-            host_coord(ch, inv_ratio, g.axs0 + a_hi, g.axs1 + b_lo, &r[1], &c[1]);
-            host_coord(ch, inv_ratio, g.axs0 + a_lo, g.axs1 + b_hi, &r[2], &c[2]);
-            host_coord(ch, inv_ratio, g.axs0 + a_hi, g.axs1 + b_hi, &r[3], &c[3]);
-            double rmin = r[0], rmax = r[0], cmin = c[0], cmax = c[0];
+            // the same 32 perimeter samples the producer warp takes (perimeter_sample)
+            double rmin = 0, rmax = 0, cmin = 0, cmax = 0;
             bool finite = true;
-            for (int i = 0; i < 4; ++i) {
-                finite = finite && std::isfinite(r[i]) && std::isfinite(c[i]);
-                rmin = std::min(rmin, r[i]); rmax = std::max(rmax, r[i]);
-                cmin = std::min(cmin, c[i]); cmax = std::max(cmax, c[i]);
+            for (int lane = 0; lane < 32; ++lane) {
+                const int j = lane & 7;
+                const bool far = (lane & 8) != 0;
+                int ca, cb;
+                if (lane < 16) { ca = far ? a_hi : a_lo; cb = b_lo + ((b_hi - b_lo) * j) / 7; }
+                else           { cb = far ? b_hi : b_lo; ca = a_lo + ((a_hi - a_lo) * j) / 7; }
+                double r, c;
+                host_coord(ch, inv_ratio, g.axs0 + ca, g.axs1 + cb, &r, &c);
+                finite = finite && std::isfinite(r) && std::isfinite(c);
+                if (lane == 0) { rmin = rmax = r; cmin = cmax = c; }
+                rmin = std::min(rmin, r); rmax = std::max(rmax, r);
+                cmin = std::min(cmin, c); cmax = std::max(cmax, c);
             }
             // tiles entirely outside the frame never gather
             if (!finite || rmax < 1.0 || cmax < 1.0 || rmin > g.sz1 || cmin > g.sz2) continue;
@@ -551,14 +587,14 @@ static void footprint(const ChainD& ch, double ratio, const RectGeom& g, int* ne
     *need2 = m2 + 2 + 3;
 }
 
-static void plan_lookup(const ChainD& ch, double ratio, const RectGeom& g, int* need1, int* need2) {
+static void plan_lookup(const ChainD& ch, double ratio, const RectGeom& g, int tl, int* need1, int* need2) {
     std::lock_guard<std::mutex> lock(g_plan_mutex);
     PlanKey key;
     memset(&key, 0, sizeof(key));
-    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
+    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0; key.tl = tl;
     for (auto& p : g_plan_cache)
         if (p.valid && memcmp(&p.key, &key, sizeof(key)) == 0) { *need1 = p.need1; *need2 = p.need2; return; }
-    footprint(ch, ratio, g, need1, need2);
+    footprint(ch, ratio, g, tl, need1, need2);
     Plan& p = g_plan_cache[g_plan_next++ % 8];
     p.key = key; p.valid = true; p.need1 = *need1; p.need2 = *need2;
 }
@@ -582,14 +618,14 @@ static EncodeTiledFn encoder(cc_ctx* ctx) {
 // Decide whether the TMA-staged variant applies and build its tensor map + tile config.
 // pxb: bytes per pixel (4: one float element; 3: three u8 elements).
 static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom& g, const void* src,
-                     int pxb, CUtensorMap* tmap, TileCfg* cfg) {
+                     int pxb, int tl, CUtensorMap* tmap, TileCfg* cfg) {
     const size_t pitch_b = (size_t)g.pitch * pxb, frame_b = (size_t)g.frame_stride * pxb;
     if ((reinterpret_cast<uintptr_t>(src) & 15u) || (pitch_b & 15u) || (g.nframes > 1 && (frame_b & 15u)))
         return false;
     EncodeTiledFn enc = encoder(ctx);
     if (!enc) return false;
     int need1, need2;
-    plan_lookup(ch, ratio, g, &need1, &need2);
+    plan_lookup(ch, ratio, g, tl, &need1, &need2);
     // box1 in pixels with a byte length that is a multiple of 16; the stage size must be a
     // multiple of 128 bytes so every stage base stays 128-byte aligned
     const int unit = (pxb == 4) ? 4 : 16;
@@ -619,8 +655,8 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     return true;
 }
 
-static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips) {
-    cfg->ntiles2 = (g.sz2 + kT - 1) / kT;
+static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips, int tl) {
+    cfg->ntiles2 = (g.sz2 + tl - 1) / tl;
     // enough CTAs for ~12 waves of 4 CTAs/SM (tail effect: profiles/r1_rectify.md sweep), but
     // walks long enough to amortise the thread setup
     const long long ctas_wanted = (long long)ctx->sm_count * 4 * 12;
@@ -628,14 +664,14 @@ static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips) {
     long long segs = (ctas_wanted + per_seg - 1) / per_seg;
     if (segs < 1) segs = 1;
     int tps = (int)((cfg->ntiles2 + segs - 1) / segs);
-    if (tps < 4) tps = std::min(4, cfg->ntiles2);
+    if (tps < 128 / tl) tps = std::min(128 / tl, cfg->ntiles2);
     if (const char* e = getenv("CAMCAL_TPS")) tps = std::max(1, atoi(e));      // tuning knob
     cfg->tiles_per_seg = std::max(tps, 1);
 }
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024)
+    if (bytes > 32 * 1024)     // static smem (barriers + headers) counts against the 48 KB default too
         CC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return CC_OK;
 }
@@ -653,25 +689,33 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     memset(&tmap, 0, sizeof(tmap));
     TileCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, &tmap, &cfg);
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, kTLf, &tmap, &cfg);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     const int strips = (sz1 + kT - 1) / kT;
-    if (!tma) cfg.stages = 1;
-    fill_cfg(&cfg, g, ctx, strips);
-    const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
-    const size_t smem = tma ? (size_t)cfg.stages * cfg.box_bytes : 0;
-    int rc = CC_OK;
-    if (tma && exact) {
-        if ((rc = set_smem(rectify_f32c1_kernel<true, true>, smem))) return rc;
-        rectify_f32c1_kernel<true, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
-    } else if (tma) {
-        if ((rc = set_smem(rectify_f32c1_kernel<false, true>, smem))) return rc;
-        rectify_f32c1_kernel<false, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
-    } else if (exact) {
-        rectify_f32c1_kernel<true, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+    if (tma) {
+        fill_cfg(&cfg, g, ctx, strips, kTLf);
+        const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
+        const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
+        if (getenv("CAMCAL_DEBUG"))
+            fprintf(stderr, "[camcal] f32c1 staged: box %dx%d (%d B) stages %d tps %d ntiles2 %d grid %u,%u,%u smem %zu\n",
+                    cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.tiles_per_seg, cfg.ntiles2, grid.x, grid.y, grid.z, smem);
+        int rc = CC_OK;
+        if (exact) {
+            if ((rc = set_smem(rectify_f32c1_kernel<true>, smem))) return rc;
+            rectify_f32c1_kernel<true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+        } else {
+            if ((rc = set_smem(rectify_f32c1_kernel<false>, smem))) return rc;
+            rectify_f32c1_kernel<false><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+        }
     } else {
-        rectify_f32c1_kernel<false, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+        // ~16 CTAs per SM worth of work, at least 32 lines per CTA
+        const long long per_line_ctas = (long long)strips * nframes;
+        long long segs = ((long long)ctx->sm_count * 64 + per_line_ctas - 1) / per_line_ctas;
+        int lines = (int)std::max<long long>(32, (sz2 + segs - 1) / std::max<long long>(segs, 1));
+        const dim3 grid(strips, (sz2 + lines - 1) / lines, nframes);
+        if (exact) rectify_f32c1_direct_kernel<true><<<grid, kConsumerThreads, 0, st>>>(pe, pf, g, lines, src, dst, fill);
+        else       rectify_f32c1_direct_kernel<false><<<grid, kConsumerThreads, 0, st>>>(pe, pf, g, lines, src, dst, fill);
     }
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
@@ -694,12 +738,12 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
     memset(&tmap, 0, sizeof(tmap));
     TileCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 3, &tmap, &cfg);
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 3, kT, &tmap, &cfg);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     const int strips = (sz1 + kT - 1) / kT;
     if (!tma) cfg.stages = 1;
-    fill_cfg(&cfg, g, ctx, strips);
+    fill_cfg(&cfg, g, ctx, strips, kT);
     const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
     const size_t smem = tma ? (size_t)cfg.stages * cfg.box_bytes : 0;
     int rc = CC_OK;

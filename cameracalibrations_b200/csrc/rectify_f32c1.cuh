@@ -1,16 +1,19 @@
-// rectify_f32c1.cuh -- fp32 single-channel rectification kernel (included by rectify.cu).
+// rectify_f32c1.cuh -- fp32 single-channel rectification kernels (included by rectify.cu).
 //
-// Per-pixel instruction budget is what bounds this kernel (profiles/r1_rectify.md), so the
-// staged path is written to the instruction:
+// The per-pixel instruction budget bounds these kernels (profiles/r1_rectify.md), so the staged
+// path is written to the instruction:
 //  * the producer folds the tile's index origin into the floor constant: the exact path adds
-//    Mk = 2^52 - K to floor(x) (or adds it with round-down, DADD.RM, which IS the floor), the
-//    fast path adds mk = 1.5*2^23 - K with FADD.RM; the low word of the sum is the tile-local
-//    tap index, and "high word == 0x43300000" / "(bits - 0x4B400000) < R" are the complete
-//    range tests (negative, NaN, huge and out-of-box coordinates all fail them);
+//    Mk = 2^52 - K to the coordinate with round-down (DADD.RM is the floor) or to
+//    FRND.F64.FLOOR(x), the fast path adds mk = 1.5*2^23 - K with FADD2.RM; the low word of the
+//    sum is magic + tile-local tap index.  "high word == 0x43300000" and
+//    "max over the batch of (bits - magic) < R" are the complete range tests (negative, NaN,
+//    huge and out-of-box coordinates all fail them), and the smem address takes the raw bits
+//    (the magic is folded into the tile's base address);
 //  * 1/P3 is NVIDIA's own correctly rounded sequence (MUFU.RCP64H + 5 DFMA) inlined without
-//    its per-pixel branch: the exponent test that guards it joins the range predicate, and a
-//    failing warp takes the generic path, which divides;
-//  * one vote per batch of lines decides between the staged gather and the generic path.
+//    its per-pixel branch: its validity test (exponent of P3 not extreme) is made once per
+//    tile by the producer on the tile corners -- P3 is affine in the output index;
+//  * one vote per batch of lines decides between the staged gather and the generic path,
+//    which lives out of line so that the hot loop keeps its registers.
 #pragma once
 
 namespace cc {
@@ -46,6 +49,21 @@ __device__ __forceinline__ float sample_direct_f32(const RectExact& pe, const Re
     }
 }
 
+// `n` consecutive lines of one lane's pixel column through the generic path (cold)
+template <bool EXACT>
+__device__ __noinline__ void generic_lines_f32(const RectExact* pe, const RectFast* pf, const RectGeom* g,
+                                               const float* __restrict__ sframe, float* __restrict__ o,
+                                               int a, int b, int n, float fill) {
+    if (a >= g->sz1) return;
+    RowTermD rtd;
+    RowTermF rtf;
+    if (EXACT) rtd = rect_row_term(*pe, g->axs0 + a); else rtf = rect_row_term(*pf, g->axs0 + a);
+    const unsigned pitch = (unsigned)g->pitch;
+    n = min(n, g->sz2 - b);
+    for (int e = 0; e < n; ++e, o += pitch)
+        __stcs(o, sample_direct_f32<EXACT>(*pe, *pf, rtd, rtf, *g, sframe, pitch, b + e, fill));
+}
+
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -58,29 +76,57 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
     return v;
 }
 
-template <bool EXACT, bool TMA>
-__global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads)
-rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
-                     const RectGeom g, const TileCfg cfg, const float* __restrict__ src,
+// ---- direct kernel: no staging (unaligned layouts, footprints too large for a box) -------
+template <bool EXACT>
+__global__ void __launch_bounds__(kConsumerThreads)
+rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_constant__ RectFast pf,
+                            const __grid_constant__ RectGeom g, const int lines_per_cta,
+                            const float* __restrict__ src, float* __restrict__ dst, float fill) {
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = blockIdx.x * kT + lane_id;
+    if (a >= g.sz1) return;
+    const int frame = blockIdx.z;
+    const float* sframe = src + (long long)frame * g.frame_stride;
+    const unsigned pitch = (unsigned)g.pitch;
+    RowTermD rtd;
+    RowTermF rtf;
+    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+    const int b_begin = blockIdx.y * lines_per_cta;
+    const int b_end = min(b_begin + lines_per_cta, g.sz2);
+    float* o = dst + (long long)frame * g.frame_stride + (long long)(b_begin + warp) * g.pitch + a;
+    for (int b = b_begin + warp; b < b_end; b += kWarps, o += (long long)kWarps * g.pitch)
+        __stcs(o, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b, fill));
+}
+
+// ---- staged kernel -------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(kConsumerThreads + 32)
+rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
+                     const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
+                     const __grid_constant__ TileCfg cfg, const float* __restrict__ src,
                      float* __restrict__ dst, float fill) {
     constexpr int KB = EXACT ? kBatchExact : kBatchFast;
+    constexpr int TL = kTLf;                      // lines per tile
+    constexpr int LPW = TL / kWarps;              // lines per warp per tile
+    static_assert(LPW % KB == 0, "batch must divide the lines of a warp");
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemCtl ctl;
-    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane_id = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int a_lo = blockIdx.x * kT;
     const int frame = blockIdx.z;
     const int t_begin = blockIdx.y * cfg.tiles_per_seg;
     const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
-    pipeline_init(&ctl, cfg.stages, TMA);
+    pipeline_init(&ctl, cfg.stages, true);
 
-    if (TMA && warp == kWarps) {                       // ---- producer warp
+    if (warp == kWarps) {                              // ---- producer warp
         if (lane_id == 0) tma_prefetch_desc(&tmap);
         int s = 0;
         uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
         for (int tile = t_begin; tile < t_end; ++tile) {
             mbar_wait(&ctl.empty[s], phase);
-            producer_tile<EXACT, 1>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
-                                    s, a_lo, tile, frame, lane_id);
+            producer_tile<EXACT, 1, TL>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
+                                        s, a_lo, tile, frame, lane_id);
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
         return;
@@ -88,127 +134,113 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact p
 
     // ---- consumer warps
     const int a = a_lo + lane_id;
-    const bool a_in = a < g.sz1;
     const float* sframe = src + (long long)frame * g.frame_stride;
     const unsigned pitch = (unsigned)g.pitch;
-    RowTermD rtd;
-    RowTermF rtf;
+    [[maybe_unused]] RowTermD rtd;
+    [[maybe_unused]] RowTermF rtf;
     const int a_c = min(a, g.sz1 - 1);                 // out-of-frame lanes shadow the last pixel
     if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-    const int line0 = t_begin * kT + warp * kLines;
+    const int line0 = t_begin * TL + warp * LPW;
     float* optr = dst + (long long)frame * g.frame_stride + (long long)line0 * g.pitch + a;
-    const long long tile_step = (long long)(kT - kLines) * g.pitch;
+    const long long tile_step = (long long)(TL - LPW) * g.pitch;
     const uint32_t box_pitch_b = (uint32_t)cfg.box1 * 4u;
-    [[maybe_unused]] const float2 fc0 = bc2(pf.Cc[0]), fc1 = bc2(pf.Cc[1]), fc2 = bc2(pf.Cc[2]);
+    const bool strip_full = a_lo + kT <= g.sz1;
 
     int s = 0;
     uint32_t phase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
-        const int b0 = tile * kT + warp * kLines;
-        const bool full_lines = (b0 + kLines <= g.sz2) && a_lo + kT <= g.sz1;
+        const int b0 = tile * TL + warp * LPW;
         const StageHdr* h = &ctl.hdr[s];
+        mbar_wait(&ctl.full[s], phase);
         [[maybe_unused]] double Mk1 = 0, Mk2 = 0;
         [[maybe_unused]] float mk1 = 0, mk2 = 0;
-        uint32_t R1 = 0, R2 = 0, base = 0;
-        if (TMA) {
-            mbar_wait(&ctl.full[s], phase);
-            if (EXACT) { Mk1 = h->Mk1; Mk2 = h->Mk2; } else { mk1 = h->mk1; mk2 = h->mk2; }
-            R1 = (uint32_t)h->R1; R2 = (uint32_t)h->R2; base = h->base;
-        }
-        // fast path: second-axis term of the first line of this warp, relative to the output centre
-        [[maybe_unused]] const float i2f = (float)(g.axs1 + b0) - pf.c2;
+        if (EXACT) { Mk1 = h->Mk1; Mk2 = h->Mk2; } else { mk1 = h->mk1; mk2 = h->mk2; }
+        uint32_t R1 = h->R1;
+        const uint32_t R2 = h->R2;
+        if (!(strip_full && b0 + LPW <= g.sz2)) R1 = 0;      // partial lines: everything generic
+        // raw magic-biased bits index the box directly: fold the bias into the base
+        const uint32_t magic = EXACT ? 0u : (uint32_t)kMagicBits;
+        const uint32_t base = h->base - magic * (box_pitch_b + 4u);
+        [[maybe_unused]] float2 ip;
+        ip.x = (float)(g.axs1 + b0) - pf.c2;
+        ip.y = ip.x + 1.0f;
+        [[maybe_unused]] const double* q2p = &h->q2[warp * LPW];
+#pragma unroll 1
+        for (int batch = 0; batch < LPW / KB; ++batch) {
+            uint32_t t1[KB], t2[KB];
+            uint32_t m1 = 0, m2 = 0;
+            [[maybe_unused]] uint32_t hi_bad = 0;
+            [[maybe_unused]] double d1d[KB], d2d[KB];
+            [[maybe_unused]] float2 d1p[KB / 2 + 1], d2p[KB / 2 + 1];
+            if (EXACT) {
 #pragma unroll
-        for (int batch = 0; batch < kLines / KB; ++batch) {
-            bool fast = false;
-            if (TMA) {
-                uint32_t l1[KB], l2[KB];
-                bool ok = full_lines;
-                [[maybe_unused]] double d1d[KB], d2d[KB];
-                [[maybe_unused]] float2 d1p[KB / 2 + 1], d2p[KB / 2 + 1];
+                for (int e = 0; e < KB; ++e) {
+                    double row, col;
+                    rect_coord_nobranch(pe, rtd, q2p[e], row, col);
+                    uint32_t h1, h2;
+                    floor_index<kFloorMode1>(row, Mk1, t1[e], h1, d1d[e]);
+                    floor_index<kFloorMode2>(col, Mk2, t2[e], h2, d2d[e]);
+                    hi_bad |= (h1 ^ 0x43300000u) | (h2 ^ 0x43300000u);
+                    m1 = max(m1, t1[e]);
+                    m2 = max(m2, t2[e]);
+                }
+                q2p += KB;
+            } else {
+#pragma unroll
+                for (int hh = 0; hh < KB / 2; ++hh) {
+                    float2 row, col;
+                    rect_coord2(pf, rtf, ip, row, col);
+                    ip = add2(ip, bc2(2.0f));
+                    floor_bits_fast2(row, mk1, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
+                    floor_bits_fast2(col, mk2, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
+                }
+#pragma unroll
+                for (int e = 0; e < KB; ++e) {
+                    m1 = max(m1, t1[e] - (uint32_t)kMagicBits);
+                    m2 = max(m2, t2[e] - (uint32_t)kMagicBits);
+                }
+            }
+            bool ok = (m1 < R1) & (m2 < R2);
+            if (EXACT) ok &= hi_bad == 0u;
+            if (__all_sync(0xffffffffu, ok)) {
+                float a00[KB], a10[KB], a01[KB], a11[KB];
+#pragma unroll
+                for (int e = 0; e < KB; ++e) {
+                    const uint32_t q = base + t2[e] * box_pitch_b + t1[e] * 4u;
+                    const uint32_t q1 = q + box_pitch_b;
+                    a00[e] = lds_f32(q); a10[e] = lds_f32_off<4>(q);
+                    a01[e] = lds_f32(q1); a11[e] = lds_f32_off<4>(q1);
+                }
+                float* o = optr;
                 if (EXACT) {
 #pragma unroll
                     for (int e = 0; e < KB; ++e) {
-                        double row, col;
-                        ok &= rect_coord_nobranch(pe, rtd, h->q2[warp * kLines + batch * KB + e], row, col);
-                        uint32_t h1, h2;
-                        floor_index<kFloorMode1>(row, Mk1, l1[e], h1, d1d[e]);
-                        floor_index<kFloorMode2>(col, Mk2, l2[e], h2, d2d[e]);
-                        ok &= ((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u;
-                        ok &= (l1[e] < R1) & (l2[e] < R2);
+                        const float v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
+                                                      (double)a11[e], d1d[e], d2d[e]);
+                        __stcs(o, v);
+                        o += pitch;
                     }
                 } else {
 #pragma unroll
                     for (int hh = 0; hh < KB / 2; ++hh) {
-                        float2 row, col;
-                        const float e0 = (float)(batch * KB + 2 * hh);
-                        rect_coord2(pf, rtf, fc0, fc1, fc2, make_float2(i2f + e0, i2f + (e0 + 1.0f)), row, col);
-                        floor_index_fast2(row, mk1, l1[2 * hh], l1[2 * hh + 1], d1p[hh]);
-                        floor_index_fast2(col, mk2, l2[2 * hh], l2[2 * hh + 1], d2p[hh]);
-                        ok &= (l1[2 * hh] < R1) & (l2[2 * hh] < R2) & (l1[2 * hh + 1] < R1) & (l2[2 * hh + 1] < R2);
+                        const float2 v = bilerp_fast2(make_float2(a00[2 * hh], a00[2 * hh + 1]),
+                                                      make_float2(a10[2 * hh], a10[2 * hh + 1]),
+                                                      make_float2(a01[2 * hh], a01[2 * hh + 1]),
+                                                      make_float2(a11[2 * hh], a11[2 * hh + 1]),
+                                                      d1p[hh], d2p[hh]);
+                        __stcs(o, v.x); __stcs(o + pitch, v.y);
+                        o += 2 * pitch;
                     }
                 }
-                fast = __all_sync(0xffffffffu, ok);
-                if (fast) {
-                    float a00[KB], a10[KB], a01[KB], a11[KB];
-#pragma unroll
-                    for (int e = 0; e < KB; ++e) {
-                        const uint32_t q = base + l2[e] * box_pitch_b + l1[e] * 4u;
-                        const uint32_t q1 = q + box_pitch_b;
-                        a00[e] = lds_f32(q); a10[e] = lds_f32_off<4>(q);
-                        a01[e] = lds_f32(q1); a11[e] = lds_f32_off<4>(q1);
-                    }
-                    float* o = optr;
-                    if (EXACT) {
-#pragma unroll
-                        for (int e = 0; e < KB; ++e) {
-                            const float v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
-                                                          (double)a11[e], d1d[e], d2d[e]);
-                            __stcs(o, v);
-                            o += pitch;
-                        }
-                    } else {
-#pragma unroll
-                        for (int hh = 0; hh < KB / 2; ++hh) {
-                            const float2 v = bilerp_fast2(make_float2(a00[2 * hh], a00[2 * hh + 1]),
-                                                          make_float2(a10[2 * hh], a10[2 * hh + 1]),
-                                                          make_float2(a01[2 * hh], a01[2 * hh + 1]),
-                                                          make_float2(a11[2 * hh], a11[2 * hh + 1]),
-                                                          d1p[hh], d2p[hh]);
-                            __stcs(o, v.x); __stcs(o + pitch, v.y);
-                            o += 2 * pitch;
-                        }
-                    }
-                }
-            }
-            if (!fast) {
-                float* o = optr;
-                const int bb = b0 + batch * KB;
-                if (TMA) {
-#pragma unroll 1
-                    for (int e = 0; e < KB; ++e) {
-                        const int b = bb + e;
-                        if (b < g.sz2 && a_in)
-                            __stcs(o, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b, fill));
-                        o += pitch;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < KB; ++e) {
-                        const int b = bb + e;
-                        if (b < g.sz2 && a_in)
-                            __stcs(o, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b, fill));
-                        o += pitch;
-                    }
-                }
+            } else {
+                generic_lines_f32<EXACT>(&pe, &pf, &g, sframe, optr, a, b0 + batch * KB, KB, fill);
             }
             optr += (long long)KB * pitch;
         }
         optr += tile_step;
-        if (TMA) {
-            __syncwarp();
-            if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
-            if (++s == cfg.stages) { s = 0; phase ^= 1; }
-        }
+        __syncwarp();
+        if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
+        if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }
 
