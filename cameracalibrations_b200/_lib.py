@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcamcal_b200.so")
+# CAMCAL_B200_LIB: load another build of the same ABI (tuning variants under profiles/variants/)
+LIB_PATH = os.environ.get("CAMCAL_B200_LIB") or os.path.join(_HERE, "libcamcal_b200.so")
 
 CC_OK = 0
 CC_ERR_INVALID_ARG = -1

@@ -242,6 +242,7 @@ int cc_ctx_destroy(cc_ctx* ctx) {
         if (ctx->pipe_out[k]) cudaFree(ctx->pipe_out[k]);
     }
     if (ctx->jtj_scratch) cudaFree(ctx->jtj_scratch);
+    rectify_free_plans(ctx);
     delete ctx;
     return CC_OK;
 }

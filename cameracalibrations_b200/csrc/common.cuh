@@ -7,6 +7,7 @@
 
 #include "../../include/camcal_b200.h"
 
+struct cc_ctx;
 namespace cc {
 
 // What `Calibration(...)` / `img2obj` derive once per view (src/meta.jl:27-33, 71-76),
@@ -25,6 +26,7 @@ using ChainF = Chain<float>;
 void rodrigues_host(const double r[3], double R[9]);
 void build_chain(const cc_intr* in, const cc_view* vw, ChainD* out);
 void narrow_chain(const ChainD& d, ChainF* f);
+void rectify_free_plans(struct ::cc_ctx* ctx);
 
 // error plumbing (abi.cu)
 int set_error(int status, const char* fmt, ...);
@@ -49,6 +51,10 @@ struct cc_ctx {
     size_t pipe_out_bytes[NSLOT];
     // TMA descriptor encode entry point (driver API, resolved at ctx creation)
     void* encode_tiled;
+    // rectification tile plans (rectify.cu: RectPlan), most recent NPLAN parameter sets
+    static const int NPLAN = 8;
+    void* rect_plans[NPLAN];
+    int rect_plan_next;
 };
 
 #define CC_CUDA(call)                                                     \

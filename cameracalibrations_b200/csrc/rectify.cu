@@ -28,7 +28,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
+#include <new>
+#include <vector>
 
 #include "rectify_device.cuh"
 #include "tma.cuh"
@@ -44,8 +45,12 @@ constexpr int kBatch = 4;              // u8c3: lines whose taps are in flight t
 #endif
 constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTLf / kWarps of them)
 constexpr int kTLmax = 64;
+#ifndef CAMCAL_WX_F32
+#define CAMCAL_WX_F32 1
+#endif
+constexpr int kWXf = CAMCAL_WX_F32;    // f32c1: consumer warps side by side along the first axis (tile width 32*kWXf)
 #ifndef CAMCAL_BATCH_EXACT
-#define CAMCAL_BATCH_EXACT 2
+#define CAMCAL_BATCH_EXACT 4
 #endif
 constexpr int kBatchExact = CAMCAL_BATCH_EXACT;   // FP64 values cost two registers each: smaller batches, more CTAs
 #ifndef CAMCAL_BATCH_FAST
@@ -61,6 +66,14 @@ constexpr int kBatchFast = CAMCAL_BATCH_FAST;
 #endif
 constexpr int kFloorMode1 = CAMCAL_FLOOR1, kFloorMode2 = CAMCAL_FLOOR2;
 constexpr int kMaxStages = 4;
+#ifndef CAMCAL_MINB
+#define CAMCAL_MINB 1
+#endif
+#ifndef CAMCAL_MINB_EXACT
+#define CAMCAL_MINB_EXACT 6
+#endif
+// __launch_bounds__ min CTAs/SM of the staged f32c1 kernels (fast / exact coordinates)
+constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
 constexpr int kConsumerThreads = 32 * kWarps;
 
 struct TileCfg {
@@ -80,6 +93,23 @@ struct __align__(16) StageHdr {
     int K1, K2;            // u8c3: fused index constants (see consumer)
     int base_off;          // u8c3: pixel offset of (lo1, lo2) inside the box
     double q2[kTLmax];     // exact path: second-axis world term of every line of the tile
+};
+
+// f32c1: per-tile header precomputed on the host (RectPlan), read straight from global memory
+struct __align__(16) TileHdr {
+    double Mk1, Mk2;       // exact: 2^52 - K   (K = global 1-based index of local tap 0)
+    float mk1, mk2;        // fast:  1.5*2^23 - K
+    uint32_t R1, R2;       // number of valid local first-tap indices per axis (0: nothing staged)
+    int x0, y0;            // box origin (0-based texel indices; may be negative)
+    uint32_t base_off;     // byte offset of local tap (0, 0) inside the stage
+    uint32_t pad;
+};
+static_assert(sizeof(TileHdr) == 48, "TileHdr is read as three 16-byte words");
+
+struct SmemRing {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    double q2[kMaxStages][kTLmax];   // exact path: second-axis world term of the lines of each staged tile
 };
 
 struct SmemCtl {
@@ -107,13 +137,13 @@ __device__ __forceinline__ void perimeter_sample(int lane_id, int a_lo, int a_hi
     }
 }
 
-template <bool EXACT, int PXB, int TL>
+template <bool EXACT, int PXB, int TL, int TW>
 __device__ __forceinline__ void producer_tile(const CUtensorMap* tmap, const RectFast& pf,
                                               const RectExact& pe, const RectGeom& g,
                                               const TileCfg& cfg, SmemCtl* ctl, uint8_t* stage,
                                               int s, int a_lo, int tile, int frame, int lane_id) {
     const int b_lo = tile * TL;
-    const int a_hi = min(a_lo + kT - 1, g.sz1 - 1), b_hi = min(b_lo + TL - 1, g.sz2 - 1);
+    const int a_hi = min(a_lo + TW - 1, g.sz1 - 1), b_hi = min(b_lo + TL - 1, g.sz2 - 1);
     int ca, cb;
     perimeter_sample(lane_id, a_lo, a_hi, b_lo, b_hi, ca, cb);
     const RowTermF rt = rect_row_term(pf, g.axs0 + ca);
@@ -324,7 +354,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe
         uint32_t phase = 1;
         for (int tile = t_begin; tile < t_end; ++tile) {
             mbar_wait(&ctl.empty[s], phase);
-            producer_tile<EXACT, 3, kT>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
+            producer_tile<EXACT, 3, kT, kT>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
                                     s, a_lo, tile, frame, lane_id);
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
@@ -543,60 +573,176 @@ static void host_coord(const ChainD& ch, double inv_ratio, long long I1, long lo
     *col = ch.fcol * radial * v + ch.ccol;
 }
 
-// Largest source footprint of any 32x32 output tile that touches the frame, from the tile
-// corners (the kernel positions each box from the same four corners).  Cached: a video
-// stream calls with the same calibration over and over.
-struct PlanKey { ChainD ch; double ratio; RectGeom g; int tl; };
-struct Plan { PlanKey key; bool valid; int need1, need2; };
-static Plan g_plan_cache[8];
-static int g_plan_next = 0;
-static std::mutex g_plan_mutex;
+// Tile plan.  For every output tile: the bounding box of its source footprint (32 samples on the
+// tile perimeter, evaluated in double) and everything the kernels derive from it.  A plan
+// depends on the calibration, ratio/axes, frame size and tile shape only -- not on the pixels --
+// so it is built once on the host, uploaded once and reused by every later call with the same
+// parameters (a video stream): the kernels' producer warp then only issues TMA loads.
+struct PlanKey { ChainD ch; double ratio; RectGeom g; int tw, tl, pxb; };
 
-static void footprint(const ChainD& ch, double ratio, const RectGeom& g, int tl, int* need1, int* need2) {
-    const double inv_ratio = 1.0 / ratio;
-    const int n1 = (g.sz1 + kT - 1) / kT, n2 = (g.sz2 + tl - 1) / tl;
+struct RectPlan {
+    PlanKey key;
+    int n1, n2;                    // tiles along the first / second axis
+    int need1, need2;              // largest footprint (pixels), incl. taps and slack
+    int box1, box2, box_bytes;     // staged box (pixels) and its size; box_bytes == 0: not stageable
+    std::vector<int> origin;       // per tile: floor(min row), floor(min col) of the perimeter samples
+    std::vector<unsigned char> p3_ok;
+    std::vector<TileHdr> hdr;      // f32c1 headers (pxb == 4)
+    std::vector<double> q2;        // exact path: second-axis world term of every output line
+    TileHdr* d_hdr;
+    double* d_q2;
+};
+
+static void plan_free(RectPlan* p) {
+    if (!p) return;
+    if (p->d_hdr) cudaFree(p->d_hdr);
+    if (p->d_q2) cudaFree(p->d_q2);
+    delete p;
+}
+
+void rectify_free_plans(cc_ctx* ctx) {
+    for (int i = 0; i < cc_ctx::NPLAN; ++i) {
+        plan_free(static_cast<RectPlan*>(ctx->rect_plans[i]));
+        ctx->rect_plans[i] = nullptr;
+    }
+}
+
+static void plan_footprints(RectPlan* p) {
+    const ChainD& ch = p->key.ch;
+    const RectGeom& g = p->key.g;
+    const int tw = p->key.tw, tl = p->key.tl;
+    const double inv_ratio = 1.0 / p->key.ratio;
+    p->n1 = (g.sz1 + tw - 1) / tw;
+    p->n2 = (g.sz2 + tl - 1) / tl;
+    p->origin.assign((size_t)p->n1 * p->n2 * 2, -4);
+    p->p3_ok.assign((size_t)p->n1 * p->n2, 1);
     int m1 = 0, m2 = 0;
-    for (int t2 = 0; t2 < n2; ++t2) {
-        const int b_lo = t2 * tl, b_hi = std::min(b_lo + tl - 1, g.sz2 - 1);
-        for (int t1 = 0; t1 < n1; ++t1) {
-            const int a_lo = t1 * kT, a_hi = std::min(a_lo + kT - 1, g.sz1 - 1);
-            // the same 32 perimeter samples the producer warp takes (perimeter_sample)
+    for (int t1 = 0; t1 < p->n1; ++t1) {
+        const int a_lo = t1 * tw, a_hi = std::min(a_lo + tw - 1, g.sz1 - 1);
+        for (int t2 = 0; t2 < p->n2; ++t2) {
+            const int b_lo = t2 * tl, b_hi = std::min(b_lo + tl - 1, g.sz2 - 1);
             double rmin = 0, rmax = 0, cmin = 0, cmax = 0;
             bool finite = true;
-            for (int lane = 0; lane < 32; ++lane) {
-                const int j = lane & 7;
-                const bool far = (lane & 8) != 0;
+            for (int j = 0; j < 32; ++j) {          // 8 samples on each of the four edges
+                const int k = j & 7;
+                const bool far = (j & 8) != 0;
                 int ca, cb;
-                if (lane < 16) { ca = far ? a_hi : a_lo; cb = b_lo + ((b_hi - b_lo) * j) / 7; }
-                else           { cb = far ? b_hi : b_lo; ca = a_lo + ((a_hi - a_lo) * j) / 7; }
+                if (j < 16) { ca = far ? a_hi : a_lo; cb = b_lo + ((b_hi - b_lo) * k) / 7; }
+                else        { cb = far ? b_hi : b_lo; ca = a_lo + ((a_hi - a_lo) * k) / 7; }
                 double r, c;
                 host_coord(ch, inv_ratio, g.axs0 + ca, g.axs1 + cb, &r, &c);
                 finite = finite && std::isfinite(r) && std::isfinite(c);
-                if (lane == 0) { rmin = rmax = r; cmin = cmax = c; }
+                if (j == 0) { rmin = rmax = r; cmin = cmax = c; }
                 rmin = std::min(rmin, r); rmax = std::max(rmax, r);
                 cmin = std::min(cmin, c); cmax = std::max(cmax, c);
             }
+            // P3 is monotone in each output index: the four corners bound it over the tile.  The
+            // branch-free reciprocal of the exact kernels needs a sane exponent and one sign.
+            double p3min = 0, p3max = 0;
+            for (int j = 0; j < 4; ++j) {
+                const long long I1 = g.axs0 + ((j & 1) ? a_hi : a_lo), I2 = g.axs1 + ((j & 2) ? b_hi : b_lo);
+                const double q1 = ((double)I1 * inv_ratio) * ch.inv_cs, q2 = ((double)I2 * inv_ratio) * ch.inv_cs;
+                const double P3 = std::fma(ch.R[7], q2, std::fma(ch.R[6], q1, ch.t[2]));
+                if (j == 0) p3min = p3max = P3;
+                p3min = std::min(p3min, P3); p3max = std::max(p3max, P3);
+            }
+            const bool p3_ok = std::isfinite(p3min) && std::isfinite(p3max) &&
+                               ((p3min > 1e-270 && p3max < 1e270) || (p3max < -1e-270 && p3min > -1e270));
+            const size_t t = (size_t)t1 * p->n2 + t2;
+            p->p3_ok[t] = p3_ok ? 1 : 0;
+            if (!finite) continue;                  // origin stays at (-4, -4): the range tests fail
+            // clamp so that far-away footprints still give a legal (fully out-of-frame) box
+            const double rc = std::min(std::max(rmin, -4.0), (double)g.sz1 + 4.0);
+            const double cc_ = std::min(std::max(cmin, -4.0), (double)g.sz2 + 4.0);
+            p->origin[2 * t] = (int)std::floor(rc);
+            p->origin[2 * t + 1] = (int)std::floor(cc_);
             // tiles entirely outside the frame never gather
-            if (!finite || rmax < 1.0 || cmax < 1.0 || rmin > g.sz1 || cmin > g.sz2) continue;
+            if (rmax < 1.0 || cmax < 1.0 || rmin > g.sz1 || cmin > g.sz2) continue;
             m1 = std::max(m1, (int)(std::floor(rmax) - std::floor(rmin)));
             m2 = std::max(m2, (int)(std::floor(cmax) - std::floor(cmin)));
         }
     }
     // taps floor-1 .. floor; 2 texels of slack below (origin) and 1 above
-    *need1 = m1 + 2 + 3;
-    *need2 = m2 + 2 + 3;
+    p->need1 = m1 + 2 + 3;
+    p->need2 = m2 + 2 + 3;
 }
 
-static void plan_lookup(const ChainD& ch, double ratio, const RectGeom& g, int tl, int* need1, int* need2) {
-    std::lock_guard<std::mutex> lock(g_plan_mutex);
+// box size from the footprint; f32c1 headers
+static void plan_boxes(RectPlan* p) {
+    const RectGeom& g = p->key.g;
+    const int pxb = p->key.pxb;
+    // box1 in pixels with a byte length that is a multiple of 16; the stage size must be a
+    // multiple of 128 bytes so every stage base stays 128-byte aligned
+    const int unit = (pxb == 4) ? 4 : 16;
+    // (+ unit - 1: the box origin is rounded down to a multiple of `unit` pixels)
+    p->box1 = (p->need1 + unit - 1 + unit - 1) / unit * unit;
+    p->box2 = p->need2;
+    while (((size_t)p->box1 * pxb * p->box2) % 128) ++p->box2;
+    const int box1_elems = (pxb == 4) ? p->box1 : p->box1 * 3;
+    p->box_bytes = p->box1 * pxb * p->box2;
+    if (box1_elems > 256 || p->box2 > 256 || p->box_bytes > 40 * 1024) p->box_bytes = 0;   // not worth staging
+    if (pxb != 4 || !p->box_bytes) return;
+    p->hdr.resize((size_t)p->n1 * p->n2);
+    for (size_t t = 0; t < p->hdr.size(); ++t) {
+        TileHdr& h = p->hdr[t];
+        memset(&h, 0, sizeof(h));
+        int x0 = p->origin[2 * t] - 2;
+        const int y0 = p->origin[2 * t + 1] - 2;
+        x0 = (x0 >= 0) ? (x0 / unit) * unit : -(((-x0) + unit - 1) / unit) * unit;
+        // valid local range of the first tap: inside the box (both taps) and inside the frame
+        const int lo1 = std::max(0, -x0), hi1 = std::min(p->box1 - 2, g.sz1 - 2 - x0);
+        const int lo2 = std::max(0, -y0), hi2 = std::min(p->box2 - 2, g.sz2 - 2 - y0);
+        h.x0 = x0; h.y0 = y0;
+        h.R1 = p->p3_ok[t] ? (uint32_t)std::max(0, hi1 - lo1 + 1) : 0u;
+        h.R2 = (uint32_t)std::max(0, hi2 - lo2 + 1);
+        const int k1 = 1 + x0 + lo1, k2 = 1 + y0 + lo2;   // global 1-based index of local tap 0
+        h.Mk1 = 4503599627370496.0 - (double)k1;
+        h.Mk2 = 4503599627370496.0 - (double)k2;
+        h.mk1 = 12582912.0f - (float)k1;
+        h.mk2 = 12582912.0f - (float)k2;
+        h.base_off = (uint32_t)(lo2 * p->box1 + lo1) * 4u;
+    }
+    p->q2.resize((size_t)g.sz2);
+    const double inv_ratio = 1.0 / p->key.ratio;
+    for (int b = 0; b < g.sz2; ++b)       // rect_q2() of rectify_device.cuh, same two products
+        p->q2[b] = ((double)((long long)g.axs1 + b) * inv_ratio) * p->key.ch.inv_cs;
+}
+
+// find or build the plan of this (calibration, geometry, tile shape); uploads on first use
+static RectPlan* plan_get(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom& g, int tw, int tl,
+                          int pxb, cudaStream_t st) {
     PlanKey key;
     memset(&key, 0, sizeof(key));
-    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0; key.tl = tl;
-    for (auto& p : g_plan_cache)
-        if (p.valid && memcmp(&p.key, &key, sizeof(key)) == 0) { *need1 = p.need1; *need2 = p.need2; return; }
-    footprint(ch, ratio, g, tl, need1, need2);
-    Plan& p = g_plan_cache[g_plan_next++ % 8];
-    p.key = key; p.valid = true; p.need1 = *need1; p.need2 = *need2;
+    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
+    key.tw = tw; key.tl = tl; key.pxb = pxb;
+    for (int i = 0; i < cc_ctx::NPLAN; ++i) {
+        RectPlan* p = static_cast<RectPlan*>(ctx->rect_plans[i]);
+        if (p && memcmp(&p->key, &key, sizeof(key)) == 0) return p;
+    }
+    RectPlan* p = new (std::nothrow) RectPlan();
+    if (!p) return nullptr;
+    p->key = key; p->d_hdr = nullptr; p->d_q2 = nullptr;
+    plan_footprints(p);
+    plan_boxes(p);
+    if (!p->hdr.empty()) {
+        const size_t hb = p->hdr.size() * sizeof(TileHdr), qb = p->q2.size() * sizeof(double);
+        if (cudaMalloc(&p->d_hdr, hb) != cudaSuccess || cudaMalloc(&p->d_q2, qb) != cudaSuccess ||
+            cudaMemcpyAsync(p->d_hdr, p->hdr.data(), hb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(p->d_q2, p->q2.data(), qb, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            cudaGetLastError();
+            plan_free(p);
+            return nullptr;
+        }
+        // later calls may come on other streams: make the tables visible to all of them
+        cudaStreamSynchronize(st);
+    }
+    const int slot = ctx->rect_plan_next++ % cc_ctx::NPLAN;
+    if (ctx->rect_plans[slot]) {
+        cudaDeviceSynchronize();       // an evicted plan may still be read by a running kernel
+        plan_free(static_cast<RectPlan*>(ctx->rect_plans[slot]));
+    }
+    ctx->rect_plans[slot] = p;
+    return p;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -618,53 +764,44 @@ static EncodeTiledFn encoder(cc_ctx* ctx) {
 // Decide whether the TMA-staged variant applies and build its tensor map + tile config.
 // pxb: bytes per pixel (4: one float element; 3: three u8 elements).
 static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom& g, const void* src,
-                     int pxb, int tl, CUtensorMap* tmap, TileCfg* cfg) {
+                     int pxb, int tw, int tl, cudaStream_t st, CUtensorMap* tmap, TileCfg* cfg,
+                     RectPlan** plan_out) {
     const size_t pitch_b = (size_t)g.pitch * pxb, frame_b = (size_t)g.frame_stride * pxb;
     if ((reinterpret_cast<uintptr_t>(src) & 15u) || (pitch_b & 15u) || (g.nframes > 1 && (frame_b & 15u)))
         return false;
     EncodeTiledFn enc = encoder(ctx);
     if (!enc) return false;
-    int need1, need2;
-    plan_lookup(ch, ratio, g, tl, &need1, &need2);
-    // box1 in pixels with a byte length that is a multiple of 16; the stage size must be a
-    // multiple of 128 bytes so every stage base stays 128-byte aligned
-    const int unit = (pxb == 4) ? 4 : 16;
-    // (+ unit - 1: the kernel rounds the box origin down to a multiple of `unit` pixels)
-    const int box1 = (need1 + unit - 1 + unit - 1) / unit * unit;
-    int box2 = need2;
-    while (((size_t)box1 * pxb * box2) % 128) ++box2;
-    const int box1_elems = (pxb == 4) ? box1 : box1 * 3;
-    if (box1_elems > 256 || box2 > 256) return false;
-    const int box_bytes = box1 * pxb * box2;
-    if (box_bytes > 40 * 1024) return false;     // footprint too large to be worth staging
-    int stages = 3;
-    if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(2, atoi(e)));   // tuning knob
-    while (stages > 2 && stages * box_bytes > 56 * 1024) --stages;
+    RectPlan* plan = plan_get(ctx, ch, ratio, g, tw, tl, pxb, st);
+    if (!plan || !plan->box_bytes) return false;
+    // measured (profiles/r1_rectify.md): occupancy beats ring depth
+    int stages = 2;
+    if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
+    while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 
+    const int box1_elems = (pxb == 4) ? plan->box1 : plan->box1 * 3;
     cuuint64_t dims[3] = {(cuuint64_t)g.sz1 * (pxb == 4 ? 1 : 3), (cuuint64_t)g.sz2,
                           (cuuint64_t)std::max(g.nframes, 1)};
     cuuint64_t strides[2] = {(cuuint64_t)pitch_b, (cuuint64_t)(g.nframes > 1 ? frame_b : pitch_b * g.sz2)};
-    cuuint32_t box[3] = {(cuuint32_t)box1_elems, (cuuint32_t)box2, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box1_elems, (cuuint32_t)plan->box2, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(tmap, pxb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                            const_cast<void*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
-    cfg->box1 = box1; cfg->box2 = box2; cfg->stages = stages; cfg->box_bytes = box_bytes;
+    cfg->box1 = plan->box1; cfg->box2 = plan->box2; cfg->stages = stages; cfg->box_bytes = plan->box_bytes;
+    *plan_out = plan;
     return true;
 }
 
 static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips, int tl) {
     cfg->ntiles2 = (g.sz2 + tl - 1) / tl;
-    // enough CTAs for ~12 waves of 4 CTAs/SM (tail effect: profiles/r1_rectify.md sweep), but
-    // walks long enough to amortise the thread setup
-    const long long ctas_wanted = (long long)ctx->sm_count * 4 * 12;
-    const long long per_seg = (long long)strips * std::max(g.nframes, 1);
-    long long segs = (ctas_wanted + per_seg - 1) / per_seg;
-    if (segs < 1) segs = 1;
-    int tps = (int)((cfg->ntiles2 + segs - 1) / segs);
-    if (tps < 128 / tl) tps = std::min(128 / tl, cfg->ntiles2);
+    // short-lived CTAs (two tiles, both loads in flight from the start) measured fastest: the
+    // SM overlaps the load latency of one CTA with the arithmetic of the others.  Longer walks
+    // only when the grid would exceed the y limit.
+    (void)ctx; (void)strips;
+    int tps = std::min(std::max(128 / tl, 1), cfg->ntiles2);
+    while ((cfg->ntiles2 + tps - 1) / tps > 65535) ++tps;
     if (const char* e = getenv("CAMCAL_TPS")) tps = std::max(1, atoi(e));      // tuning knob
     cfg->tiles_per_seg = std::max(tps, 1);
 }
@@ -689,11 +826,13 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     memset(&tmap, 0, sizeof(tmap));
     TileCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, kTLf, &tmap, &cfg);
+    RectPlan* plan = nullptr;
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, kT * kWXf, kTLf, st, &tmap, &cfg, &plan);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
-    const int strips = (sz1 + kT - 1) / kT;
+    int strips = (sz1 + kT - 1) / kT;
     if (tma) {
+        strips = (sz1 + kT * kWXf - 1) / (kT * kWXf);
         fill_cfg(&cfg, g, ctx, strips, kTLf);
         const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
@@ -703,10 +842,10 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
         int rc = CC_OK;
         if (exact) {
             if ((rc = set_smem(rectify_f32c1_kernel<true>, smem))) return rc;
-            rectify_f32c1_kernel<true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+            rectify_f32c1_kernel<true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, src, dst, fill);
         } else {
             if ((rc = set_smem(rectify_f32c1_kernel<false>, smem))) return rc;
-            rectify_f32c1_kernel<false><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, fill);
+            rectify_f32c1_kernel<false><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, src, dst, fill);
         }
     } else {
         // ~16 CTAs per SM worth of work, at least 32 lines per CTA
@@ -738,7 +877,8 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
     memset(&tmap, 0, sizeof(tmap));
     TileCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 3, kT, &tmap, &cfg);
+    RectPlan* plan = nullptr;
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 3, kT, kT, st, &tmap, &cfg, &plan);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     const int strips = (sz1 + kT - 1) / kT;

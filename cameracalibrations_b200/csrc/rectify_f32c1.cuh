@@ -50,8 +50,16 @@ __device__ __forceinline__ float sample_direct_f32(const RectExact& pe, const Re
 }
 
 // `n` consecutive lines of one lane's pixel column through the generic path (cold)
+#ifndef CAMCAL_GENERIC_INLINE
+#define CAMCAL_GENERIC_INLINE 1
+#endif
+#if CAMCAL_GENERIC_INLINE
+#define CC_GENERIC_ATTR __forceinline__
+#else
+#define CC_GENERIC_ATTR __noinline__
+#endif
 template <bool EXACT>
-__device__ __noinline__ void generic_lines_f32(const RectExact* pe, const RectFast* pf, const RectGeom* g,
+__device__ CC_GENERIC_ATTR void generic_lines_f32(const RectExact* pe, const RectFast* pf, const RectGeom* g,
                                                const float* __restrict__ sframe, float* __restrict__ o,
                                                int a, int b, int n, float fill) {
     if (a >= g->sz1) return;
@@ -60,6 +68,7 @@ __device__ __noinline__ void generic_lines_f32(const RectExact* pe, const RectFa
     if (EXACT) rtd = rect_row_term(*pe, g->axs0 + a); else rtf = rect_row_term(*pf, g->axs0 + a);
     const unsigned pitch = (unsigned)g->pitch;
     n = min(n, g->sz2 - b);
+#pragma unroll 1
     for (int e = 0; e < n; ++e, o += pitch)
         __stcs(o, sample_direct_f32<EXACT>(*pe, *pf, rtd, rtf, *g, sframe, pitch, b + e, fill));
 }
@@ -99,72 +108,112 @@ rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_c
 }
 
 // ---- staged kernel -------------------------------------------------------------------------
+// Producer warp: waits for a free stage, reads the tile's box origin from the plan and issues
+// ONE cp.async.bulk.tensor; for the exact kernel it also copies the q2 terms of the tile's lines
+// next to the barriers.  Consumer warps: read the tile header from the plan (three 16-byte
+// uniform loads, issued before the barrier wait), then gather from the staged box.
+__device__ __forceinline__ void ring_init(SmemRing* ring, int stages) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&ring->full[s], 1);
+            mbar_init(&ring->empty[s], kWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
 template <bool EXACT>
-__global__ void __launch_bounds__(kConsumerThreads + 32)
+__global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
                      const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
-                     const __grid_constant__ TileCfg cfg, const float* __restrict__ src,
+                     const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
+                     const double* __restrict__ q2tab, const float* __restrict__ src,
                      float* __restrict__ dst, float fill) {
     constexpr int KB = EXACT ? kBatchExact : kBatchFast;
     constexpr int TL = kTLf;                      // lines per tile
-    constexpr int LPW = TL / kWarps;              // lines per warp per tile
+    constexpr int WX = kWXf, WY = kWarps / WX;    // consumer warps across / down the tile
+    constexpr int LPW = TL / WY;                  // lines per warp per tile
     static_assert(LPW % KB == 0, "batch must divide the lines of a warp");
     extern __shared__ __align__(128) uint8_t stage_mem[];
-    __shared__ SmemCtl ctl;
+    __shared__ SmemRing ring;
     const int lane_id = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
-    const int a_lo = blockIdx.x * kT;
+    const int a_lo = blockIdx.x * (kT * WX);
     const int frame = blockIdx.z;
     const int t_begin = blockIdx.y * cfg.tiles_per_seg;
     const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
-    pipeline_init(&ctl, cfg.stages, true);
+    const TileHdr* hp = plan + (size_t)blockIdx.x * cfg.ntiles2 + t_begin;
+    ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
         if (lane_id == 0) tma_prefetch_desc(&tmap);
         int s = 0;
         uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
-        for (int tile = t_begin; tile < t_end; ++tile) {
-            mbar_wait(&ctl.empty[s], phase);
-            producer_tile<EXACT, 1, TL>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
-                                        s, a_lo, tile, frame, lane_id);
+        for (int tile = t_begin; tile < t_end; ++tile, ++hp) {
+            const int2 origin = __ldg(reinterpret_cast<const int2*>(&hp->x0));
+            [[maybe_unused]] double q2a = 0, q2b = 0;
+            if (EXACT) {
+                const int b = tile * TL + lane_id;
+                q2a = __ldg(q2tab + min(b, g.sz2 - 1));
+                if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
+            }
+            mbar_wait(&ring.empty[s], phase);
+            if (EXACT) {
+                if (lane_id < TL) ring.q2[s][lane_id] = q2a;
+                if (TL > 32) ring.q2[s][lane_id + 32] = q2b;
+                __syncwarp();
+            }
+            if (lane_id == 0) {
+                mbar_arrive_expect_tx(&ring.full[s], (uint32_t)cfg.box_bytes);
+                tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, &tmap, &ring.full[s], origin.x, origin.y, frame);
+            }
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
         return;
     }
 
     // ---- consumer warps
-    const int a = a_lo + lane_id;
+    const int wx = warp % WX, wy = warp / WX;
+    const int a = a_lo + wx * kT + lane_id;
     const float* sframe = src + (long long)frame * g.frame_stride;
     const unsigned pitch = (unsigned)g.pitch;
     [[maybe_unused]] RowTermD rtd;
     [[maybe_unused]] RowTermF rtf;
     const int a_c = min(a, g.sz1 - 1);                 // out-of-frame lanes shadow the last pixel
     if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-    const int line0 = t_begin * TL + warp * LPW;
+    const int line0 = t_begin * TL + wy * LPW;
     float* optr = dst + (long long)frame * g.frame_stride + (long long)line0 * g.pitch + a;
     const long long tile_step = (long long)(TL - LPW) * g.pitch;
     const uint32_t box_pitch_b = (uint32_t)cfg.box1 * 4u;
-    const bool strip_full = a_lo + kT <= g.sz1;
+    const bool strip_full = a_lo + (wx + 1) * kT <= g.sz1;
+    const uint32_t stage0 = smem_u32(stage_mem);
 
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const int b0 = tile * TL + warp * LPW;
-        const StageHdr* h = &ctl.hdr[s];
-        mbar_wait(&ctl.full[s], phase);
+    for (int tile = t_begin; tile < t_end; ++tile, ++hp) {
+        const int b0 = tile * TL + wy * LPW;
+        // header: {Mk1, Mk2} {mk1, mk2, R1, R2} {x0, y0, base_off, pad}
         [[maybe_unused]] double Mk1 = 0, Mk2 = 0;
         [[maybe_unused]] float mk1 = 0, mk2 = 0;
-        if (EXACT) { Mk1 = h->Mk1; Mk2 = h->Mk2; } else { mk1 = h->mk1; mk2 = h->mk2; }
-        uint32_t R1 = h->R1;
-        const uint32_t R2 = h->R2;
+        if (EXACT) {
+            const double2 hA = __ldg(reinterpret_cast<const double2*>(hp));
+            Mk1 = hA.x; Mk2 = hA.y;
+        }
+        const uint4 hB = __ldg(reinterpret_cast<const uint4*>(hp) + 1);
+        const uint32_t base_off = __ldg(&hp->base_off);
+        if (!EXACT) { mk1 = __uint_as_float(hB.x); mk2 = __uint_as_float(hB.y); }
+        uint32_t R1 = hB.z;
+        const uint32_t R2 = hB.w;
         if (!(strip_full && b0 + LPW <= g.sz2)) R1 = 0;      // partial lines: everything generic
         // raw magic-biased bits index the box directly: fold the bias into the base
         const uint32_t magic = EXACT ? 0u : (uint32_t)kMagicBits;
-        const uint32_t base = h->base - magic * (box_pitch_b + 4u);
+        const uint32_t base = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes + base_off - magic * (box_pitch_b + 4u);
         [[maybe_unused]] float2 ip;
         ip.x = (float)(g.axs1 + b0) - pf.c2;
         ip.y = ip.x + 1.0f;
-        [[maybe_unused]] const double* q2p = &h->q2[warp * LPW];
+        [[maybe_unused]] const double* q2p = &ring.q2[s][wy * LPW];
+        mbar_wait(&ring.full[s], phase);
 #pragma unroll 1
         for (int batch = 0; batch < LPW / KB; ++batch) {
             uint32_t t1[KB], t2[KB];
@@ -239,7 +288,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         }
         optr += tile_step;
         __syncwarp();
-        if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
+        if (lane_id == 0) mbar_arrive(&ring.empty[s]);
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }

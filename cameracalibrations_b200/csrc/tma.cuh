@@ -37,9 +37,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 // Polling costs issue slots that other CTAs on the SM could use: back off between probes.
+#ifndef CAMCAL_WAIT_SLEEP
+#define CAMCAL_WAIT_SLEEP 256
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+    while (!mbar_try_wait(bar, parity)) {
+        if (CAMCAL_WAIT_SLEEP > 0) __nanosleep(CAMCAL_WAIT_SLEEP);
+    }
 }
 
 // 3-D tiled tensor load global -> shared, completion signalled on an mbarrier

@@ -1,2 +1,5 @@
-for tps in 8 15 30 60; do for st in 2 3 4; do
-for c in f32; do CAMCAL_TPS=$tps CAMCAL_STAGES=$st python bench.py --workload c2 --steps 30 --warmup 5 --no-cpu --no-extras --coord $c --gather tma 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c2 tps=$tps stages=$st $c', round(d['ms_per_step'],3), round(d['roofline']['frac'],3))"; done; done; done
+#!/bin/bash
+for so in "" profiles/variants/lib_sleep0.so profiles/variants/lib_sleep32.so; do
+for st in 2 3; do for tps in 2 8 30; do
+  CAMCAL_B200_LIB=${so:+$PWD/$so} CAMCAL_STAGES=$st CAMCAL_TPS=$tps python profiles/ktime.py c2 f32 2>&1 | grep -v Warning | sed "s/^/st=$st tps=$tps /"
+done; done; done
