@@ -243,6 +243,7 @@ int cc_ctx_destroy(cc_ctx* ctx) {
     }
     if (ctx->jtj_scratch) cudaFree(ctx->jtj_scratch);
     rectify_free_plans(ctx);
+    rectify_free_sched(ctx);
     delete ctx;
     return CC_OK;
 }

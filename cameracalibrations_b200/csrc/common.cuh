@@ -27,6 +27,7 @@ void rodrigues_host(const double r[3], double R[9]);
 void build_chain(const cc_intr* in, const cc_view* vw, ChainD* out);
 void narrow_chain(const ChainD& d, ChainF* f);
 void rectify_free_plans(struct ::cc_ctx* ctx);
+void rectify_free_sched(struct ::cc_ctx* ctx);
 
 // error plumbing (abi.cu)
 int set_error(int status, const char* fmt, ...);
@@ -55,6 +56,13 @@ struct cc_ctx {
     static const int NPLAN = 8;
     void* rect_plans[NPLAN];
     int rect_plan_next;
+    // ticket counters of the persistent rectification kernels (rectify.cu: RectSched)
+    static const int NSCHED = 16;
+    void* sched_pool;
+    cudaEvent_t sched_event[NSCHED];
+    cudaStream_t sched_stream[NSCHED];
+    unsigned char sched_used[NSCHED];
+    unsigned sched_next;
 };
 
 #define CC_CUDA(call)                                                     \

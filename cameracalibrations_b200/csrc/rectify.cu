@@ -66,11 +66,15 @@ constexpr int kBatchFast = CAMCAL_BATCH_FAST;
 #endif
 constexpr int kFloorMode1 = CAMCAL_FLOOR1, kFloorMode2 = CAMCAL_FLOOR2;
 constexpr int kMaxStages = 4;
+#ifndef CAMCAL_PRODUCER_SLEEP
+#define CAMCAL_PRODUCER_SLEEP 256
+#endif
+constexpr int kProducerSleep = CAMCAL_PRODUCER_SLEEP;   // ns between the producer's probes of a full ring
 #ifndef CAMCAL_MINB
 #define CAMCAL_MINB 1
 #endif
 #ifndef CAMCAL_MINB_EXACT
-#define CAMCAL_MINB_EXACT 6
+#define CAMCAL_MINB_EXACT 5
 #endif
 // __launch_bounds__ min CTAs/SM of the staged f32c1 kernels (fast / exact coordinates)
 constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
@@ -82,6 +86,9 @@ struct TileCfg {
     int tiles_per_seg;     // tiles one CTA walks
     int ntiles2;           // tiles along the second axis
     int box_bytes;         // bytes one TMA load delivers = stage stride (multiple of 128)
+    // persistent f32c1 kernels: work units (strip x, tile y, frame z), x fastest
+    int strips;            // tiles along the first axis
+    uint32_t units;        // strips * ntiles2 * nframes
 };
 
 // per-stage header written by the producer warp
@@ -106,11 +113,17 @@ struct __align__(16) TileHdr {
 };
 static_assert(sizeof(TileHdr) == 48, "TileHdr is read as three 16-byte words");
 
+// per-stage slot of the persistent f32c1 kernels, published by the producer warp
 struct SmemRing {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
+    int4 pos[kMaxStages];            // (strip x, tile y, frame z, -); z < 0: no more work
+    TileHdr hdr[kMaxStages];
     double q2[kMaxStages][kTLmax];   // exact path: second-axis world term of the lines of each staged tile
 };
+
+// global ticket counter of one launch (self-resetting: the last producer zeroes it)
+struct RectSched { uint32_t next, done; };
 
 struct SmemCtl {
     uint64_t full[kMaxStages];
@@ -774,7 +787,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     RectPlan* plan = plan_get(ctx, ch, ratio, g, tw, tl, pxb, st);
     if (!plan || !plan->box_bytes) return false;
     // measured (profiles/r1_rectify.md): occupancy beats ring depth
-    int stages = 2;
+    int stages = (pxb == 4) ? 3 : 2;
     if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
     while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 
@@ -813,6 +826,37 @@ static int set_smem(K kernel, size_t bytes) {
     return CC_OK;
 }
 
+// Ticket counters: a small ring of self-resetting counters per context.  Launches on different
+// streams may overlap, so consecutive launches take different counters, and a counter is only
+// handed out again after the launch that used it last has finished (event wait on the new stream).
+static int sched_acquire(cc_ctx* ctx, cudaStream_t st, RectSched** out) {
+    if (!ctx->sched_pool) {
+        CC_CUDA(cudaMalloc(&ctx->sched_pool, cc_ctx::NSCHED * sizeof(RectSched)));
+        CC_CUDA(cudaMemset(ctx->sched_pool, 0, cc_ctx::NSCHED * sizeof(RectSched)));
+        for (int i = 0; i < cc_ctx::NSCHED; ++i)
+            CC_CUDA(cudaEventCreateWithFlags(&ctx->sched_event[i], cudaEventDisableTiming));
+    }
+    const int slot = ctx->sched_next % cc_ctx::NSCHED;
+    if (ctx->sched_used[slot] && ctx->sched_stream[slot] != st)
+        CC_CUDA(cudaStreamWaitEvent(st, ctx->sched_event[slot], 0));
+    *out = static_cast<RectSched*>(ctx->sched_pool) + slot;
+    return CC_OK;
+}
+
+static void sched_release(cc_ctx* ctx, cudaStream_t st) {
+    const int slot = ctx->sched_next++ % cc_ctx::NSCHED;
+    cudaEventRecord(ctx->sched_event[slot], st);
+    ctx->sched_used[slot] = 1;
+    ctx->sched_stream[slot] = st;
+}
+
+void rectify_free_sched(cc_ctx* ctx) {
+    if (!ctx->sched_pool) return;
+    for (int i = 0; i < cc_ctx::NSCHED; ++i) cudaEventDestroy(ctx->sched_event[i]);
+    cudaFree(ctx->sched_pool);
+    ctx->sched_pool = nullptr;
+}
+
 int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int64_t axs_min[2],
                          const float* src, float* dst, int sz1, int sz2, size_t pitch,
                          size_t frame_stride, int nframes, float fill, unsigned flags,
@@ -833,20 +877,32 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     int strips = (sz1 + kT - 1) / kT;
     if (tma) {
         strips = (sz1 + kT * kWXf - 1) / (kT * kWXf);
-        fill_cfg(&cfg, g, ctx, strips, kTLf);
-        const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
+        cfg.ntiles2 = (sz2 + kTLf - 1) / kTLf;
+        cfg.strips = strips;
+        CC_REQUIRE((unsigned long long)strips * cfg.ntiles2 * nframes < (1ull << 31), "too many tiles in one call: split the batch");
+        cfg.units = (uint32_t)strips * (uint32_t)cfg.ntiles2 * (uint32_t)nframes;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
-        if (getenv("CAMCAL_DEBUG"))
-            fprintf(stderr, "[camcal] f32c1 staged: box %dx%d (%d B) stages %d tps %d ntiles2 %d grid %u,%u,%u smem %zu\n",
-                    cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.tiles_per_seg, cfg.ntiles2, grid.x, grid.y, grid.z, smem);
-        int rc = CC_OK;
+        int rc = CC_OK, per_sm = 0;
         if (exact) {
             if ((rc = set_smem(rectify_f32c1_kernel<true>, smem))) return rc;
-            rectify_f32c1_kernel<true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, src, dst, fill);
+            CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rectify_f32c1_kernel<true>, kConsumerThreads + 32, smem));
         } else {
             if ((rc = set_smem(rectify_f32c1_kernel<false>, smem))) return rc;
-            rectify_f32c1_kernel<false><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, src, dst, fill);
+            CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rectify_f32c1_kernel<false>, kConsumerThreads + 32, smem));
         }
+        if (const char* e = getenv("CAMCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // tuning knob
+        // persistent grid: every CTA slot of the device, round-robin over the units
+        const uint32_t gsz = std::min<uint32_t>(cfg.units, (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1));
+        RectSched* sched = nullptr;
+        if ((rc = sched_acquire(ctx, st, &sched))) return rc;
+        if (getenv("CAMCAL_DEBUG"))
+            fprintf(stderr, "[camcal] f32c1 staged: box %dx%d (%d B) stages %d units %u grid %u (%d/SM) smem %zu\n",
+                    cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.units, gsz, per_sm, smem);
+        if (exact)
+            rectify_f32c1_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+        else
+            rectify_f32c1_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+        sched_release(ctx, st);
     } else {
         // ~16 CTAs per SM worth of work, at least 32 lines per CTA
         const long long per_line_ctas = (long long)strips * nframes;

@@ -108,10 +108,18 @@ rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_c
 }
 
 // ---- staged kernel -------------------------------------------------------------------------
-// Producer warp: waits for a free stage, reads the tile's box origin from the plan and issues
-// ONE cp.async.bulk.tensor; for the exact kernel it also copies the q2 terms of the tile's lines
-// next to the barriers.  Consumer warps: read the tile header from the plan (three 16-byte
-// uniform loads, issued before the barrier wait), then gather from the staged box.
+// Persistent CTAs fed from a global ticket counter.  A work unit is one tile (strip x, tile y,
+// frame z), numbered x fastest, and units are handed out in that order to whichever CTA has a
+// free stage: at any instant the device works on a window of consecutive units, so tiles that
+// share source lines (the halos of neighbouring strips) are fetched within microseconds of each
+// other and the second fetch hits L2.  Static schedules (long private walks, round-robin) let
+// the CTAs drift apart and were measured to read 1.5x the frame from DRAM
+// (profiles/r1_rectify.md).
+//
+// Producer warp, per unit: take a ticket (one ticket ahead, so the atomic's latency is hidden),
+// decode it, read the tile header and the q2 terms from the plan, wait for a free stage, publish
+// {position, header, q2} in the stage's slot and issue ONE cp.async.bulk.tensor.  A ticket past
+// the last unit is published as a stop marker.  The last producer to leave resets the counter.
 __device__ __forceinline__ void ring_init(SmemRing* ring, int stages) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -123,13 +131,19 @@ __device__ __forceinline__ void ring_init(SmemRing* ring, int stages) {
     __syncthreads();
 }
 
+__device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
+    uint32_t u = 0;
+    if (lane_id == 0) u = atomicAdd(&sched->next, 1u);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
                      const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
                      const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
-                     const double* __restrict__ q2tab, const float* __restrict__ src,
-                     float* __restrict__ dst, float fill) {
+                     const double* __restrict__ q2tab, RectSched* __restrict__ sched,
+                     const float* __restrict__ src, float* __restrict__ dst, float fill) {
     constexpr int KB = EXACT ? kBatchExact : kBatchFast;
     constexpr int TL = kTLf;                      // lines per tile
     constexpr int WX = kWXf, WY = kWarps / WX;    // consumer warps across / down the tile
@@ -139,81 +153,95 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     __shared__ SmemRing ring;
     const int lane_id = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
-    const int a_lo = blockIdx.x * (kT * WX);
-    const int frame = blockIdx.z;
-    const int t_begin = blockIdx.y * cfg.tiles_per_seg;
-    const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
-    const TileHdr* hp = plan + (size_t)blockIdx.x * cfg.ntiles2 + t_begin;
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
         if (lane_id == 0) tma_prefetch_desc(&tmap);
         int s = 0;
         uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
-        for (int tile = t_begin; tile < t_end; ++tile, ++hp) {
-            const int2 origin = __ldg(reinterpret_cast<const int2*>(&hp->x0));
+        uint32_t u_next = take_ticket(sched, lane_id);
+        for (;;) {
+            const uint32_t u = u_next;
+            const bool live = u < cfg.units;
+            int x = 0, y = 0, z = 0;
+            uint32_t hword = 0;
             [[maybe_unused]] double q2a = 0, q2b = 0;
-            if (EXACT) {
-                const int b = tile * TL + lane_id;
-                q2a = __ldg(q2tab + min(b, g.sz2 - 1));
-                if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
+            if (live) {
+                x = (int)(u % (uint32_t)cfg.strips);
+                const uint32_t r = u / (uint32_t)cfg.strips;
+                y = (int)(r % (uint32_t)cfg.ntiles2);
+                z = (int)(r / (uint32_t)cfg.ntiles2);
+                const uint32_t* hp = reinterpret_cast<const uint32_t*>(plan + x * cfg.ntiles2 + y);
+                if (lane_id < 12) hword = __ldg(hp + lane_id);        // the 48-byte header, one word per lane
+                if (EXACT) {
+                    const int b = y * TL + lane_id;
+                    q2a = __ldg(q2tab + min(b, g.sz2 - 1));
+                    if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
+                }
+                u_next = take_ticket(sched, lane_id);
             }
-            mbar_wait(&ring.empty[s], phase);
+            mbar_wait<kProducerSleep>(&ring.empty[s], phase);
+            if (!live) {
+                if (lane_id == 0) { ring.pos[s] = make_int4(0, 0, -1, 0); mbar_arrive(&ring.full[s]); }
+                break;
+            }
+            if (lane_id < 12) reinterpret_cast<uint32_t*>(&ring.hdr[s])[lane_id] = hword;
+            if (lane_id == 12) ring.pos[s] = make_int4(x, y, z, 0);
             if (EXACT) {
                 if (lane_id < TL) ring.q2[s][lane_id] = q2a;
                 if (TL > 32) ring.q2[s][lane_id + 32] = q2b;
-                __syncwarp();
             }
+            const int x0 = __shfl_sync(0xffffffffu, (int)hword, 8), y0 = __shfl_sync(0xffffffffu, (int)hword, 9);
+            __syncwarp();
             if (lane_id == 0) {
                 mbar_arrive_expect_tx(&ring.full[s], (uint32_t)cfg.box_bytes);
-                tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, &tmap, &ring.full[s], origin.x, origin.y, frame);
+                tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, &tmap, &ring.full[s], x0, y0, z);
             }
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
+        }
+        // every producer has taken its last ticket before it counts itself out
+        if (lane_id == 0 && atomicAdd(&sched->done, 1u) == gridDim.x - 1) {
+            sched->next = 0;
+            sched->done = 0;
         }
         return;
     }
 
     // ---- consumer warps
     const int wx = warp % WX, wy = warp / WX;
-    const int a = a_lo + wx * kT + lane_id;
-    const float* sframe = src + (long long)frame * g.frame_stride;
     const unsigned pitch = (unsigned)g.pitch;
-    [[maybe_unused]] RowTermD rtd;
-    [[maybe_unused]] RowTermF rtf;
-    const int a_c = min(a, g.sz1 - 1);                 // out-of-frame lanes shadow the last pixel
-    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-    const int line0 = t_begin * TL + wy * LPW;
-    float* optr = dst + (long long)frame * g.frame_stride + (long long)line0 * g.pitch + a;
-    const long long tile_step = (long long)(TL - LPW) * g.pitch;
     const uint32_t box_pitch_b = (uint32_t)cfg.box1 * 4u;
-    const bool strip_full = a_lo + (wx + 1) * kT <= g.sz1;
     const uint32_t stage0 = smem_u32(stage_mem);
 
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++hp) {
-        const int b0 = tile * TL + wy * LPW;
-        // header: {Mk1, Mk2} {mk1, mk2, R1, R2} {x0, y0, base_off, pad}
+    for (;;) {
+        mbar_wait(&ring.full[s], phase);
+        const int4 pos = ring.pos[s];
+        if (pos.z < 0) break;
+        const TileHdr* h = &ring.hdr[s];
+        const int a_w = pos.x * (kT * WX) + wx * kT;           // first pixel of this warp's lanes
+        const int a = a_w + lane_id;
+        const int b0 = pos.y * TL + wy * LPW;
+        const float* sframe = src + (long long)pos.z * g.frame_stride;
+        float* optr = dst + (long long)pos.z * g.frame_stride + (long long)b0 * g.pitch + a;
+        [[maybe_unused]] RowTermD rtd;
+        [[maybe_unused]] RowTermF rtf;
+        const int a_c = min(a, g.sz1 - 1);             // out-of-frame lanes shadow the last pixel
+        if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
         [[maybe_unused]] double Mk1 = 0, Mk2 = 0;
         [[maybe_unused]] float mk1 = 0, mk2 = 0;
-        if (EXACT) {
-            const double2 hA = __ldg(reinterpret_cast<const double2*>(hp));
-            Mk1 = hA.x; Mk2 = hA.y;
-        }
-        const uint4 hB = __ldg(reinterpret_cast<const uint4*>(hp) + 1);
-        const uint32_t base_off = __ldg(&hp->base_off);
-        if (!EXACT) { mk1 = __uint_as_float(hB.x); mk2 = __uint_as_float(hB.y); }
-        uint32_t R1 = hB.z;
-        const uint32_t R2 = hB.w;
-        if (!(strip_full && b0 + LPW <= g.sz2)) R1 = 0;      // partial lines: everything generic
+        if (EXACT) { Mk1 = h->Mk1; Mk2 = h->Mk2; } else { mk1 = h->mk1; mk2 = h->mk2; }
+        uint32_t R1 = h->R1;
+        const uint32_t R2 = h->R2;
+        if (!(a_w + kT <= g.sz1 && b0 + LPW <= g.sz2)) R1 = 0;   // partial lines: everything generic
         // raw magic-biased bits index the box directly: fold the bias into the base
         const uint32_t magic = EXACT ? 0u : (uint32_t)kMagicBits;
-        const uint32_t base = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes + base_off - magic * (box_pitch_b + 4u);
+        const uint32_t base = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes + h->base_off - magic * (box_pitch_b + 4u);
         [[maybe_unused]] float2 ip;
         ip.x = (float)(g.axs1 + b0) - pf.c2;
         ip.y = ip.x + 1.0f;
         [[maybe_unused]] const double* q2p = &ring.q2[s][wy * LPW];
-        mbar_wait(&ring.full[s], phase);
 #pragma unroll 1
         for (int batch = 0; batch < LPW / KB; ++batch) {
             uint32_t t1[KB], t2[KB];
@@ -286,7 +314,6 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             }
             optr += (long long)KB * pitch;
         }
-        optr += tile_step;
         __syncwarp();
         if (lane_id == 0) mbar_arrive(&ring.empty[s]);
         if (++s == cfg.stages) { s = 0; phase ^= 1; }

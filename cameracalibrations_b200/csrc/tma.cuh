@@ -40,10 +40,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef CAMCAL_WAIT_SLEEP
 #define CAMCAL_WAIT_SLEEP 256
 #endif
+template <int SLEEP_NS = CAMCAL_WAIT_SLEEP>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     while (!mbar_try_wait(bar, parity)) {
-        if (CAMCAL_WAIT_SLEEP > 0) __nanosleep(CAMCAL_WAIT_SLEEP);
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     }
 }
 
