@@ -38,13 +38,15 @@ namespace cc {
 
 constexpr int kT = 32;                 // strip width along the first axis = lanes of a warp
 constexpr int kWarps = 4;              // consumer warps per CTA
-constexpr int kLines = kT / kWarps;    // u8c3: lines per warp per (32-line) tile
-constexpr int kBatch = 4;              // u8c3: lines whose taps are in flight together
 #ifndef CAMCAL_TL_F32
 #define CAMCAL_TL_F32 64
 #endif
 constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTLf / kWarps of them)
 constexpr int kTLmax = 64;
+#ifndef CAMCAL_TL_U8
+#define CAMCAL_TL_U8 64
+#endif
+constexpr int kTLu = CAMCAL_TL_U8;     // u8c3: lines per tile
 #ifndef CAMCAL_WX_F32
 #define CAMCAL_WX_F32 1
 #endif
@@ -78,28 +80,23 @@ constexpr int kProducerSleep = CAMCAL_PRODUCER_SLEEP;   // ns between the produc
 #endif
 // __launch_bounds__ min CTAs/SM of the staged f32c1 kernels (fast / exact coordinates)
 constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
+#ifndef CAMCAL_MINB_U8
+#define CAMCAL_MINB_U8 1
+#endif
+#ifndef CAMCAL_MINB_U8_EXACT
+#define CAMCAL_MINB_U8_EXACT 1
+#endif
+constexpr int kMinBlocksU8 = CAMCAL_MINB_U8, kMinBlocksU8Exact = CAMCAL_MINB_U8_EXACT;
 constexpr int kConsumerThreads = 32 * kWarps;
 
 struct TileCfg {
     int box1, box2;        // staged box, in pixels (box1 along the contiguous axis)
     int stages;
-    int tiles_per_seg;     // tiles one CTA walks
     int ntiles2;           // tiles along the second axis
     int box_bytes;         // bytes one TMA load delivers = stage stride (multiple of 128)
     // persistent f32c1 kernels: work units (strip x, tile y, frame z), x fastest
     int strips;            // tiles along the first axis
     uint32_t units;        // strips * ntiles2 * nframes
-};
-
-// per-stage header written by the producer warp
-struct __align__(16) StageHdr {
-    double Mk1, Mk2;       // exact: 2^52 - K   (K = global 1-based index of local tap 0)
-    float mk1, mk2;        // fast:  1.5*2^23 - K
-    uint32_t R1, R2;       // number of valid local first-tap indices per axis (0: nothing staged)
-    uint32_t base;         // shared-memory byte address of local tap (0, 0) (f32c1)
-    int K1, K2;            // u8c3: fused index constants (see consumer)
-    int base_off;          // u8c3: pixel offset of (lo1, lo2) inside the box
-    double q2[kTLmax];     // exact path: second-axis world term of every line of the tile
 };
 
 // f32c1: per-tile header precomputed on the host (RectPlan), read straight from global memory
@@ -108,7 +105,7 @@ struct __align__(16) TileHdr {
     float mk1, mk2;        // fast:  1.5*2^23 - K
     uint32_t R1, R2;       // number of valid local first-tap indices per axis (0: nothing staged)
     int x0, y0;            // box origin (0-based texel indices; may be negative)
-    uint32_t base_off;     // byte offset of local tap (0, 0) inside the stage
+    uint32_t base_off;     // byte offset of local tap (0, 0) inside the stage (pixels are 4 or 3 bytes)
     uint32_t pad;
 };
 static_assert(sizeof(TileHdr) == 48, "TileHdr is read as three 16-byte words");
@@ -125,375 +122,11 @@ struct SmemRing {
 // global ticket counter of one launch (self-resetting: the last producer zeroes it)
 struct RectSched { uint32_t next, done; };
 
-struct SmemCtl {
-    uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
-    StageHdr hdr[kMaxStages];
-};
-
-// --------------------------------------------------------------------------------------
-// producer: box origin from 32 samples on the tile perimeter (FP32 map, even for the exact
-// kernels -- it only positions the box), header, TMA issue.
-// PXB = 1 (f32c1 elements) or 3 (u8c3 bytes); TL = lines per tile.
-// --------------------------------------------------------------------------------------
-__device__ __forceinline__ void perimeter_sample(int lane_id, int a_lo, int a_hi, int b_lo, int b_hi,
-                                                 int& ca, int& cb) {
-    // lanes 0-15: the two edges a = a_lo / a_hi, 8 samples each; lanes 16-31: b = b_lo / b_hi
-    const int j = lane_id & 7;
-    const bool far = (lane_id & 8) != 0;
-    if (lane_id < 16) {
-        ca = far ? a_hi : a_lo;
-        cb = b_lo + ((b_hi - b_lo) * j) / 7;
-    } else {
-        cb = far ? b_hi : b_lo;
-        ca = a_lo + ((a_hi - a_lo) * j) / 7;
-    }
-}
-
-template <bool EXACT, int PXB, int TL, int TW>
-__device__ __forceinline__ void producer_tile(const CUtensorMap* tmap, const RectFast& pf,
-                                              const RectExact& pe, const RectGeom& g,
-                                              const TileCfg& cfg, SmemCtl* ctl, uint8_t* stage,
-                                              int s, int a_lo, int tile, int frame, int lane_id) {
-    const int b_lo = tile * TL;
-    const int a_hi = min(a_lo + TW - 1, g.sz1 - 1), b_hi = min(b_lo + TL - 1, g.sz2 - 1);
-    int ca, cb;
-    perimeter_sample(lane_id, a_lo, a_hi, b_lo, b_hi, ca, cb);
-    const RowTermF rt = rect_row_term(pf, g.axs0 + ca);
-    float row, col;
-    rect_coord(pf, rt, (float)(g.axs1 + cb) - pf.c2, row, col);
-    // clamp so that NaN / far-away footprints still give a legal (fully out-of-frame) box
-    row = fminf(fmaxf(row, -4.0f), (float)g.sz1 + 4.0f);
-    col = fminf(fmaxf(col, -4.0f), (float)g.sz2 + 4.0f);
-    int r0 = (row == row) ? (int)floorf(row) : -4;
-    int c0 = (col == col) ? (int)floorf(col) : -4;
-    r0 = __reduce_min_sync(0xffffffffu, r0);
-    c0 = __reduce_min_sync(0xffffffffu, c0);
-    // the branch-free reciprocal of the exact consumers needs a sane exponent: P3 is monotone in
-    // each output index, so the four corners bound it over the tile (same FP64 formula)
-    bool p3_ok = true;
-    if (EXACT) {
-        const int ka = (lane_id & 1) ? a_hi : a_lo, kb = (lane_id & 2) ? b_hi : b_lo;
-        const RowTermD rd = rect_row_term(pe, g.axs0 + ka);
-        const double P3 = fma(pe.R1[2], rect_q2(pe, g.axs1 + kb), rd.B3);
-        const bool sane = fabs(P3) >= 1e-270 && fabs(P3) <= 1e270;
-        p3_ok = __all_sync(0xffffffffu, sane) &&
-                (__all_sync(0xffffffffu, P3 > 0.0) || __all_sync(0xffffffffu, P3 < 0.0));
-    }
-    // first tap index is floor - 1 (0-based); one texel of slack for the FP32 estimate.
-    // The first-axis origin is rounded down so that the byte address stays 16-byte aligned.
-    int x0 = r0 - 2;
-    const int y0 = c0 - 2;
-    constexpr int kAlign = (PXB == 1) ? 4 : 16;
-    x0 = (x0 >= 0) ? (x0 / kAlign) * kAlign : -(((-x0) + kAlign - 1) / kAlign) * kAlign;
-    StageHdr* h = &ctl->hdr[s];
-    if (EXACT) {
-#pragma unroll
-        for (int i = 0; i < TL / 32; ++i) h->q2[lane_id + 32 * i] = rect_q2(pe, g.axs1 + b_lo + lane_id + 32 * i);
-    }
-    if (lane_id == 0) {
-        // valid local range of the first tap: inside the box (both taps) and inside the frame
-        const int lo1 = max(0, -x0), hi1 = min(cfg.box1 - 2, g.sz1 - 2 - x0);
-        const int lo2 = max(0, -y0), hi2 = min(cfg.box2 - 2, g.sz2 - 2 - y0);
-        h->K1 = (EXACT ? 1 : kMagicBits + 1) + x0 + lo1;
-        h->K2 = (EXACT ? 1 : kMagicBits + 1) + y0 + lo2;
-        h->R1 = p3_ok ? (uint32_t)max(0, hi1 - lo1 + 1) : 0u;
-        h->R2 = (uint32_t)max(0, hi2 - lo2 + 1);
-        h->base_off = lo2 * cfg.box1 + lo1;
-        const int k1 = 1 + x0 + lo1, k2 = 1 + y0 + lo2;
-        h->Mk1 = 4503599627370496.0 - (double)k1;
-        h->Mk2 = 4503599627370496.0 - (double)k2;
-        h->mk1 = 12582912.0f - (float)k1;
-        h->mk2 = 12582912.0f - (float)k2;
-        h->base = smem_u32(stage) + (uint32_t)(lo2 * cfg.box1 + lo1) * (PXB == 1 ? 4u : 3u);
-    }
-    __syncwarp();
-    if (lane_id == 0) {
-        mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)cfg.box_bytes);
-        tma_load_3d(stage, tmap, &ctl->full[s], x0 * PXB, y0, frame);
-    }
-}
-
-__device__ __forceinline__ void pipeline_init(SmemCtl* ctl, int stages, bool tma) {
-    if (tma && threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(&ctl->full[s], 1);
-            mbar_init(&ctl->empty[s], kWarps);
-        }
-        mbar_fence_init();
-    }
-    if (tma) __syncthreads();
-}
-
 }  // namespace cc
+#include "rectify_ring.cuh"
 #include "rectify_f32c1.cuh"
+#include "rectify_u8c3.cuh"
 namespace cc {
-
-// --------------------------------------------------------------------------------------
-// u8 x 3 interleaved (RGB{N0f8}).  Each tap is 3 bytes at byte offset 3*i; the two taps of
-// one source line are 6 contiguous bytes, fetched as three aligned 32-bit words and
-// funnelled with PRMT.  The staged box is a byte tensor (first axis = 3*pixels).
-// --------------------------------------------------------------------------------------
-struct Taps6 { uint32_t lo, hi; };   // bytes [o, o+4) and [o+4, o+8) of a byte stream
-
-template <typename LD>
-__device__ __forceinline__ Taps6 load6(const uint32_t* words, unsigned o, unsigned sel, LD ld) {
-    const uint32_t* w = words + (o >> 2);
-    const uint32_t w0 = ld(w), w1 = ld(w + 1), w2 = ld(w + 2);
-    Taps6 t;
-    t.lo = __byte_perm(w0, w1, sel);
-    t.hi = __byte_perm(w1, w2, sel);
-    return t;
-}
-__device__ __forceinline__ unsigned sel6(unsigned o) { return 0x3210u + 0x1111u * (o & 3u); }
-
-// byte k of w as a float without a conversion instruction: 0x4B000000 | b  ==  2^23 + b
-__device__ __forceinline__ float byte_f(uint32_t w, int k) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + (unsigned)k)) - 8388608.0f;
-}
-__device__ __forceinline__ double byte_d(uint32_t w, int k) { return (double)((w >> (8 * k)) & 0xffu); }
-
-// t0 = source line i2, t1 = line i2+1;  t.lo = [a00.r a00.g a00.b a10.r], t.hi = [a10.g a10.b . .]
-template <bool EXACT>
-__device__ __forceinline__ uint32_t blend_rgb(const Taps6& t0, const Taps6& t1, double d1d, double d2d,
-                                              float d1f, float d2f) {
-    uint32_t r, g, b;
-    if (EXACT) {
-        r = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 0), byte_d(t0.lo, 3), byte_d(t1.lo, 0), byte_d(t1.lo, 3), d1d, d2d));
-        g = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 1), byte_d(t0.hi, 0), byte_d(t1.lo, 1), byte_d(t1.hi, 0), d1d, d2d));
-        b = (uint32_t)(int)rint(bilerp(byte_d(t0.lo, 2), byte_d(t0.hi, 1), byte_d(t1.lo, 2), byte_d(t1.hi, 1), d1d, d2d));
-    } else {
-        // round-to-nearest by magic add; weights in [0,1] keep the result inside [0,255]
-        const float m = 12582912.0f;
-        const float fr = bilerp_fast(byte_f(t0.lo, 0), byte_f(t0.lo, 3), byte_f(t1.lo, 0), byte_f(t1.lo, 3), d1f, d2f) + m;
-        const float fg = bilerp_fast(byte_f(t0.lo, 1), byte_f(t0.hi, 0), byte_f(t1.lo, 1), byte_f(t1.hi, 0), d1f, d2f) + m;
-        const float fb = bilerp_fast(byte_f(t0.lo, 2), byte_f(t0.hi, 1), byte_f(t1.lo, 2), byte_f(t1.hi, 1), d1f, d2f) + m;
-        r = __float_as_uint(fr); g = __float_as_uint(fg); b = __float_as_uint(fb);
-    }
-    // low bytes of r, g, b -> 0x00BBGGRR
-    return __byte_perm(__byte_perm(r, g, 0x0040), b, 0x0410);
-}
-
-// two pixels at once (FADD2/FFMA2): same arithmetic as blend_rgb<false>
-__device__ __forceinline__ float2 byte_f2(uint32_t wp, uint32_t wq, int k) {
-    return add2(make_float2(__uint_as_float(__byte_perm(wp, 0x4B000000u, 0x7440u + (unsigned)k)),
-                            __uint_as_float(__byte_perm(wq, 0x4B000000u, 0x7440u + (unsigned)k))),
-                bc2(-8388608.0f));
-}
-__device__ __forceinline__ void blend_rgb2(const Taps6& p0, const Taps6& p1, const Taps6& q0,
-                                           const Taps6& q1, float2 d1, float2 d2, uint32_t& rgb_p,
-                                           uint32_t& rgb_q) {
-    const float2 m = bc2(12582912.0f);
-    const float2 fr = add2(bilerp_fast2(byte_f2(p0.lo, q0.lo, 0), byte_f2(p0.lo, q0.lo, 3),
-                                        byte_f2(p1.lo, q1.lo, 0), byte_f2(p1.lo, q1.lo, 3), d1, d2), m);
-    const float2 fg = add2(bilerp_fast2(byte_f2(p0.lo, q0.lo, 1), byte_f2(p0.hi, q0.hi, 0),
-                                        byte_f2(p1.lo, q1.lo, 1), byte_f2(p1.hi, q1.hi, 0), d1, d2), m);
-    const float2 fb = add2(bilerp_fast2(byte_f2(p0.lo, q0.lo, 2), byte_f2(p0.hi, q0.hi, 1),
-                                        byte_f2(p1.lo, q1.lo, 2), byte_f2(p1.hi, q1.hi, 1), d1, d2), m);
-    rgb_p = __byte_perm(__byte_perm(__float_as_uint(fr.x), __float_as_uint(fg.x), 0x0040), __float_as_uint(fb.x), 0x0410);
-    rgb_q = __byte_perm(__byte_perm(__float_as_uint(fr.y), __float_as_uint(fg.y), 0x0040), __float_as_uint(fb.y), 0x0410);
-}
-
-__device__ __forceinline__ void store_rgb(uint8_t* q, uint32_t rgb) {
-    q[0] = (uint8_t)rgb; q[1] = (uint8_t)(rgb >> 8); q[2] = (uint8_t)(rgb >> 16);
-}
-
-// generic per-pixel path with every check and direct global taps
-template <bool EXACT>
-__device__ __forceinline__ uint32_t sample_direct_u8(const RectExact& pe, const RectFast& pf,
-                                                     const RowTermD& rtd, const RowTermF& rtf,
-                                                     const RectGeom& g, const uint8_t* __restrict__ sframe,
-                                                     unsigned pitch3, unsigned frame_bytes, int b,
-                                                     uint32_t fill) {
-    int g1, g2;
-    double d1d = 0, d2d = 0;
-    float d1f = 0, d2f = 0;
-    if (EXACT) {
-        double row, col;
-        rect_coord(pe, rtd, rect_q2(pe, g.axs1 + b), row, col);
-        if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) return fill;
-        lin_floor(row, g1, d1d);
-        lin_floor(col, g2, d2d);
-        lin_fix_edge(g.sz1, g1, d1d);
-        lin_fix_edge(g.sz2, g2, d2d);
-        g1 -= 1; g2 -= 1;
-    } else {
-        float row, col;
-        int t1, t2;
-        rect_coord(pf, rtf, (float)(g.axs1 + b) - pf.c2, row, col);
-        lin_floor_fast(row, t1, d1f);
-        lin_floor_fast(col, t2, d2f);
-        g1 = t1 - (kMagicBits + 1); g2 = t2 - (kMagicBits + 1);
-        if (!(((unsigned)g1 <= (unsigned)(g.sz1 - 2)) & ((unsigned)g2 <= (unsigned)(g.sz2 - 2)))) return fill;
-    }
-    const unsigned off = (unsigned)g2 * pitch3 + (unsigned)g1 * 3u;
-    Taps6 t0, t1;
-    // word-granular gather from a 4-byte aligned base; the byte path for the last few taps of
-    // the frame so nothing outside the caller's buffer is touched
-    if (off + pitch3 + 12u <= frame_bytes) {
-        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(sframe) & 3u);
-        const uint32_t* gwords = reinterpret_cast<const uint32_t*>(sframe - mis);
-        auto ld = [](const uint32_t* p) { return __ldg(p); };
-        t0 = load6(gwords, off + mis, sel6(off + mis), ld);
-        t1 = load6(gwords, off + pitch3 + mis, sel6(off + pitch3 + mis), ld);
-    } else {
-        const uint8_t* q = sframe + off;
-        t0.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-        t0.hi = q[4] | (q[5] << 8);
-        q += pitch3;
-        t1.lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
-        t1.hi = q[4] | (q[5] << 8);
-    }
-    return blend_rgb<EXACT>(t0, t1, d1d, d2d, d1f, d2f);
-}
-
-template <bool EXACT, bool TMA>
-__global__ void __launch_bounds__(TMA ? kConsumerThreads + 32 : kConsumerThreads)
-rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const RectExact pe, const RectFast pf,
-                    const RectGeom g, const TileCfg cfg, const uint8_t* __restrict__ src,
-                    uint8_t* __restrict__ dst, uchar3 fill3, unsigned frame_bytes) {
-    extern __shared__ __align__(128) uint8_t stage_mem[];
-    __shared__ SmemCtl ctl;
-    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int a_lo = blockIdx.x * kT;
-    const int frame = blockIdx.z;
-    const int t_begin = blockIdx.y * cfg.tiles_per_seg;
-    const int t_end = min(t_begin + cfg.tiles_per_seg, cfg.ntiles2);
-    pipeline_init(&ctl, cfg.stages, TMA);
-
-    if (TMA && warp == kWarps) {
-        if (lane_id == 0) tma_prefetch_desc(&tmap);
-        int s = 0;
-        uint32_t phase = 1;
-        for (int tile = t_begin; tile < t_end; ++tile) {
-            mbar_wait(&ctl.empty[s], phase);
-            producer_tile<EXACT, 3, kT, kT>(&tmap, pf, pe, g, cfg, &ctl, stage_mem + (size_t)s * cfg.box_bytes,
-                                    s, a_lo, tile, frame, lane_id);
-            if (++s == cfg.stages) { s = 0; phase ^= 1; }
-        }
-        return;
-    }
-
-    const int a = a_lo + lane_id;
-    const bool a_in = a < g.sz1;
-    const int a_c = min(a, g.sz1 - 1);
-    const uint8_t* sframe = src + (long long)frame * g.frame_stride * 3;
-    const unsigned pitch3 = (unsigned)g.pitch * 3u;
-    const unsigned box_pitch = (unsigned)cfg.box1 * 3u;           // bytes per box line (multiple of 48)
-    const uint32_t fill = fill3.x | (fill3.y << 8) | (fill3.z << 16);
-    RowTermD rtd;
-    RowTermF rtf;
-    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-    const int line0 = t_begin * kT + warp * kLines;
-    uint8_t* optr = dst + ((long long)frame * g.frame_stride + (long long)line0 * g.pitch + a) * 3;
-    float i2f = (float)(g.axs1 + line0) - pf.c2;
-    const long long tile_step = (long long)(kT - kLines) * g.pitch * 3;
-    auto ld_shared = [](const uint32_t* p) { return *p; };
-
-    int s = 0;
-    uint32_t phase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const int b0 = tile * kT + warp * kLines;
-        const bool full_lines = b0 + kLines <= g.sz2;
-        int K1 = 0, R1 = 0, K2 = 0, R2 = 0;
-        const uint32_t* box = nullptr;
-        unsigned box_off = 0;
-        const StageHdr* h = &ctl.hdr[s];
-#pragma unroll
-        for (int batch = 0; batch < kLines / kBatch; ++batch) {
-            const int bb = b0 + batch * kBatch;
-            bool fast = false;
-            if (TMA) {
-                int t1[kBatch], t2[kBatch];
-                bool guard = true;
-                [[maybe_unused]] double d1d[kBatch], d2d[kBatch];
-                [[maybe_unused]] float2 d1p[kBatch / 2], d2p[kBatch / 2];
-                if (EXACT) {
-                    if (batch == 0) mbar_wait(&ctl.full[s], phase);
-#pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        double row, col;
-                        rect_coord(pe, rtd, h->q2[warp * kLines + batch * kBatch + e], row, col);
-                        lin_floor(row, t1[e], d1d[e]);
-                        lin_floor(col, t2[e], d2d[e]);
-                        const unsigned h1 = (unsigned)__double2hiint(row) - 0x3FF00000u;
-                        const unsigned h2 = (unsigned)__double2hiint(col) - 0x3FF00000u;
-                        guard &= (h1 < 0x01F00000u) & (h2 < 0x01F00000u);
-                    }
-                } else {
-#pragma unroll
-                    for (int hh = 0; hh < kBatch / 2; ++hh) {
-                        float2 row, col;
-                        const float base = i2f + (float)(batch * kBatch + 2 * hh);
-                        rect_coord2(pf, rtf, make_float2(base, base + 1.0f), row, col);
-                        lin_floor_fast2(row, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
-                        lin_floor_fast2(col, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
-                    }
-                }
-                if (batch == 0) {
-                    if (!EXACT) mbar_wait(&ctl.full[s], phase);
-                    K1 = h->K1; R1 = (int)h->R1; K2 = h->K2; R2 = (int)h->R2;
-                    box = reinterpret_cast<const uint32_t*>(stage_mem + (size_t)s * cfg.box_bytes);
-                    box_off = (unsigned)h->base_off * 3u;   // base_off = lo2*box1 + lo1 (pixels)
-                }
-                unsigned o[kBatch];
-                bool staged = guard;
-#pragma unroll
-                for (int e = 0; e < kBatch; ++e) {
-                    const int l1 = t1[e] - K1, l2 = t2[e] - K2;
-                    staged &= ((unsigned)l1 < (unsigned)R1) & ((unsigned)l2 < (unsigned)R2);
-                    o[e] = box_off + (unsigned)l2 * box_pitch + (unsigned)l1 * 3u;
-                }
-                fast = full_lines && __all_sync(0xffffffffu, staged);
-                if (fast) {
-                    uint8_t* q = optr;
-                    Taps6 ta[kBatch], tb[kBatch];
-#pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        const unsigned sel = sel6(o[e]);          // box_pitch % 4 == 0: same for both lines
-                        ta[e] = load6(box, o[e], sel, ld_shared);
-                        tb[e] = load6(box, o[e] + box_pitch, sel, ld_shared);
-                    }
-                    if (EXACT) {
-#pragma unroll
-                        for (int e = 0; e < kBatch; ++e) {
-                            const uint32_t rgb = blend_rgb<true>(ta[e], tb[e], d1d[e], d2d[e], 0.f, 0.f);
-                            if (a_in) store_rgb(q, rgb);
-                            q += pitch3;
-                        }
-                    } else {
-#pragma unroll
-                        for (int hh = 0; hh < kBatch / 2; ++hh) {
-                            uint32_t rgb0, rgb1;
-                            blend_rgb2(ta[2 * hh], tb[2 * hh], ta[2 * hh + 1], tb[2 * hh + 1], d1p[hh],
-                                       d2p[hh], rgb0, rgb1);
-                            if (a_in) { store_rgb(q, rgb0); store_rgb(q + pitch3, rgb1); }
-                            q += 2 * pitch3;
-                        }
-                    }
-                }
-            }
-            if (!fast) {
-                uint8_t* q = optr;
-#pragma unroll
-                for (int e = 0; e < kBatch; ++e) {
-                    const int b = bb + e;
-                    if (b < g.sz2 && a_in)
-                        store_rgb(q, sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b, fill));
-                    q += pitch3;
-                }
-            }
-            optr += (long long)kBatch * pitch3;
-        }
-        i2f += (float)kT;
-        optr += tile_step;
-        if (TMA) {
-            __syncwarp();
-            if (lane_id == 0) mbar_arrive(&ctl.empty[s]);
-            if (++s == cfg.stages) { s = 0; phase ^= 1; }
-        }
-    }
-}
 
 // --------------------------------------------------------------------------------------
 // the map alone (FP64): the source coordinate each output pixel samples
@@ -506,8 +139,8 @@ rectify_map_kernel(const RectExact p, const RectGeom g, double* __restrict__ map
     if (a >= g.sz1) return;
     const RowTermD rt = rect_row_term(p, g.axs0 + a);
 #pragma unroll
-    for (int e = 0; e < kLines; ++e) {
-        const int b = blockIdx.y * kT + warp * kLines + e;
+    for (int e = 0; e < kT / kWarps; ++e) {
+        const int b = blockIdx.y * kT + warp * (kT / kWarps) + e;
         if (b < g.sz2) {
             double row, col;
             rect_coord(p, rt, rect_q2(p, g.axs1 + b), row, col);
@@ -600,7 +233,7 @@ struct RectPlan {
     int box1, box2, box_bytes;     // staged box (pixels) and its size; box_bytes == 0: not stageable
     std::vector<int> origin;       // per tile: floor(min row), floor(min col) of the perimeter samples
     std::vector<unsigned char> p3_ok;
-    std::vector<TileHdr> hdr;      // f32c1 headers (pxb == 4)
+    std::vector<TileHdr> hdr;      // tile headers
     std::vector<double> q2;        // exact path: second-axis world term of every output line
     TileHdr* d_hdr;
     double* d_q2;
@@ -680,7 +313,7 @@ static void plan_footprints(RectPlan* p) {
     p->need2 = m2 + 2 + 3;
 }
 
-// box size from the footprint; f32c1 headers
+// box size from the footprint; tile headers
 static void plan_boxes(RectPlan* p) {
     const RectGeom& g = p->key.g;
     const int pxb = p->key.pxb;
@@ -694,7 +327,7 @@ static void plan_boxes(RectPlan* p) {
     const int box1_elems = (pxb == 4) ? p->box1 : p->box1 * 3;
     p->box_bytes = p->box1 * pxb * p->box2;
     if (box1_elems > 256 || p->box2 > 256 || p->box_bytes > 40 * 1024) p->box_bytes = 0;   // not worth staging
-    if (pxb != 4 || !p->box_bytes) return;
+    if (!p->box_bytes) return;
     p->hdr.resize((size_t)p->n1 * p->n2);
     for (size_t t = 0; t < p->hdr.size(); ++t) {
         TileHdr& h = p->hdr[t];
@@ -713,7 +346,7 @@ static void plan_boxes(RectPlan* p) {
         h.Mk2 = 4503599627370496.0 - (double)k2;
         h.mk1 = 12582912.0f - (float)k1;
         h.mk2 = 12582912.0f - (float)k2;
-        h.base_off = (uint32_t)(lo2 * p->box1 + lo1) * 4u;
+        h.base_off = (uint32_t)(lo2 * p->box1 + lo1) * (uint32_t)pxb;
     }
     p->q2.resize((size_t)g.sz2);
     const double inv_ratio = 1.0 / p->key.ratio;
@@ -787,7 +420,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     RectPlan* plan = plan_get(ctx, ch, ratio, g, tw, tl, pxb, st);
     if (!plan || !plan->box_bytes) return false;
     // measured (profiles/r1_rectify.md): occupancy beats ring depth
-    int stages = (pxb == 4) ? 3 : 2;
+    int stages = 2;
     if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
     while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 
@@ -805,18 +438,6 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     cfg->box1 = plan->box1; cfg->box2 = plan->box2; cfg->stages = stages; cfg->box_bytes = plan->box_bytes;
     *plan_out = plan;
     return true;
-}
-
-static void fill_cfg(TileCfg* cfg, const RectGeom& g, cc_ctx* ctx, int strips, int tl) {
-    cfg->ntiles2 = (g.sz2 + tl - 1) / tl;
-    // short-lived CTAs (two tiles, both loads in flight from the start) measured fastest: the
-    // SM overlaps the load latency of one CTA with the arithmetic of the others.  Longer walks
-    // only when the grid would exceed the y limit.
-    (void)ctx; (void)strips;
-    int tps = std::min(std::max(128 / tl, 1), cfg->ntiles2);
-    while ((cfg->ntiles2 + tps - 1) / tps > 65535) ++tps;
-    if (const char* e = getenv("CAMCAL_TPS")) tps = std::max(1, atoi(e));      // tuning knob
-    cfg->tiles_per_seg = std::max(tps, 1);
 }
 
 template <typename K>
@@ -857,6 +478,38 @@ void rectify_free_sched(cc_ctx* ctx) {
     ctx->sched_pool = nullptr;
 }
 
+// persistent grid of a staged kernel: every CTA slot of the device (tickets do the balancing)
+template <typename K>
+static int persistent_grid(cc_ctx* ctx, K kernel, size_t smem, const TileCfg& cfg, uint32_t* gsz) {
+    int rc = set_smem(kernel, smem), per_sm = 0;
+    if (rc) return rc;
+    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kConsumerThreads + 32, smem));
+    if (const char* e = getenv("CAMCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // tuning knob
+    *gsz = std::min<uint32_t>(cfg.units, (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1));
+    if (getenv("CAMCAL_DEBUG"))
+        fprintf(stderr, "[camcal] staged: box %dx%d (%d B) stages %d units %u grid %u (%d/SM) smem %zu\n",
+                cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.units, *gsz, per_sm, smem);
+    return CC_OK;
+}
+
+static int unit_cfg(TileCfg* cfg, int sz1, int sz2, int nframes, int tw, int tl) {
+    cfg->strips = (sz1 + tw - 1) / tw;
+    cfg->ntiles2 = (sz2 + tl - 1) / tl;
+    CC_REQUIRE((unsigned long long)cfg->strips * cfg->ntiles2 * nframes < (1ull << 31),
+               "too many tiles in one call: split the batch");
+    cfg->units = (uint32_t)cfg->strips * (uint32_t)cfg->ntiles2 * (uint32_t)nframes;
+    return CC_OK;
+}
+
+// grid of the direct (unstaged) kernels: ~64 CTAs per SM worth of work, at least 32 lines per CTA
+static dim3 direct_grid(cc_ctx* ctx, int sz1, int sz2, int nframes, int* lines) {
+    const int strips = (sz1 + kT - 1) / kT;
+    const long long per_line_ctas = (long long)strips * nframes;
+    const long long segs = std::max<long long>(1, ((long long)ctx->sm_count * 64 + per_line_ctas - 1) / per_line_ctas);
+    *lines = (int)std::max<long long>(32, (sz2 + segs - 1) / segs);
+    return dim3(strips, (sz2 + *lines - 1) / *lines, nframes);
+}
+
 int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int64_t axs_min[2],
                          const float* src, float* dst, int sz1, int sz2, size_t pitch,
                          size_t frame_stride, int nframes, float fill, unsigned flags,
@@ -874,41 +527,23 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, kT * kWXf, kTLf, st, &tmap, &cfg, &plan);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
-    int strips = (sz1 + kT - 1) / kT;
+    int rc = CC_OK;
     if (tma) {
-        strips = (sz1 + kT * kWXf - 1) / (kT * kWXf);
-        cfg.ntiles2 = (sz2 + kTLf - 1) / kTLf;
-        cfg.strips = strips;
-        CC_REQUIRE((unsigned long long)strips * cfg.ntiles2 * nframes < (1ull << 31), "too many tiles in one call: split the batch");
-        cfg.units = (uint32_t)strips * (uint32_t)cfg.ntiles2 * (uint32_t)nframes;
+        if ((rc = unit_cfg(&cfg, sz1, sz2, nframes, kT * kWXf, kTLf))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
-        int rc = CC_OK, per_sm = 0;
-        if (exact) {
-            if ((rc = set_smem(rectify_f32c1_kernel<true>, smem))) return rc;
-            CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rectify_f32c1_kernel<true>, kConsumerThreads + 32, smem));
-        } else {
-            if ((rc = set_smem(rectify_f32c1_kernel<false>, smem))) return rc;
-            CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rectify_f32c1_kernel<false>, kConsumerThreads + 32, smem));
-        }
-        if (const char* e = getenv("CAMCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // tuning knob
-        // persistent grid: every CTA slot of the device, round-robin over the units
-        const uint32_t gsz = std::min<uint32_t>(cfg.units, (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1));
+        uint32_t gsz = 0;
+        if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, &gsz)
+                        : persistent_grid(ctx, rectify_f32c1_kernel<false>, smem, cfg, &gsz))) return rc;
         RectSched* sched = nullptr;
         if ((rc = sched_acquire(ctx, st, &sched))) return rc;
-        if (getenv("CAMCAL_DEBUG"))
-            fprintf(stderr, "[camcal] f32c1 staged: box %dx%d (%d B) stages %d units %u grid %u (%d/SM) smem %zu\n",
-                    cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.units, gsz, per_sm, smem);
         if (exact)
             rectify_f32c1_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
         else
             rectify_f32c1_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
         sched_release(ctx, st);
     } else {
-        // ~16 CTAs per SM worth of work, at least 32 lines per CTA
-        const long long per_line_ctas = (long long)strips * nframes;
-        long long segs = ((long long)ctx->sm_count * 64 + per_line_ctas - 1) / per_line_ctas;
-        int lines = (int)std::max<long long>(32, (sz2 + segs - 1) / std::max<long long>(segs, 1));
-        const dim3 grid(strips, (sz2 + lines - 1) / lines, nframes);
+        int lines = 0;
+        const dim3 grid = direct_grid(ctx, sz1, sz2, nframes, &lines);
         if (exact) rectify_f32c1_direct_kernel<true><<<grid, kConsumerThreads, 0, st>>>(pe, pf, g, lines, src, dst, fill);
         else       rectify_f32c1_direct_kernel<false><<<grid, kConsumerThreads, 0, st>>>(pe, pf, g, lines, src, dst, fill);
     }
@@ -934,25 +569,32 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
     TileCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
     RectPlan* plan = nullptr;
-    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 3, kT, kT, st, &tmap, &cfg, &plan);
+    // the staged kernel writes whole 32-bit words: 4-byte aligned output lines
+    const bool dst_ok = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0 && ((pitch * 3) & 3u) == 0 &&
+                        (nframes <= 1 || ((frame_stride * 3) & 3u) == 0);
+    const bool tma = !(flags & CC_GATHER_DIRECT) && dst_ok &&
+                     plan_tma(ctx, chd, ratio, g, src, 3, kT, kTLu, st, &tmap, &cfg, &plan);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
-    const int strips = (sz1 + kT - 1) / kT;
-    if (!tma) cfg.stages = 1;
-    fill_cfg(&cfg, g, ctx, strips, kT);
-    const dim3 grid(strips, (cfg.ntiles2 + cfg.tiles_per_seg - 1) / cfg.tiles_per_seg, nframes);
-    const size_t smem = tma ? (size_t)cfg.stages * cfg.box_bytes : 0;
     int rc = CC_OK;
-    if (tma && exact) {
-        if ((rc = set_smem(rectify_u8c3_kernel<true, true>, smem))) return rc;
-        rectify_u8c3_kernel<true, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
-    } else if (tma) {
-        if ((rc = set_smem(rectify_u8c3_kernel<false, true>, smem))) return rc;
-        rectify_u8c3_kernel<false, true><<<grid, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
-    } else if (exact) {
-        rectify_u8c3_kernel<true, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
+    if (tma) {
+        if ((rc = unit_cfg(&cfg, sz1, sz2, nframes, kT, kTLu))) return rc;
+        const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
+        uint32_t gsz = 0;
+        if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, &gsz)
+                        : persistent_grid(ctx, rectify_u8c3_kernel<false>, smem, cfg, &gsz))) return rc;
+        RectSched* sched = nullptr;
+        if ((rc = sched_acquire(ctx, st, &sched))) return rc;
+        if (exact)
+            rectify_u8c3_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, f, frame_bytes);
+        else
+            rectify_u8c3_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, f, frame_bytes);
+        sched_release(ctx, st);
     } else {
-        rectify_u8c3_kernel<false, false><<<grid, kConsumerThreads, 0, st>>>(tmap, pe, pf, g, cfg, src, dst, f, frame_bytes);
+        int lines = 0;
+        const dim3 grid = direct_grid(ctx, sz1, sz2, nframes, &lines);
+        if (exact) rectify_u8c3_direct_kernel<true><<<grid, kConsumerThreads, 0, st>>>(pe, pf, g, lines, src, dst, f, frame_bytes);
+        else       rectify_u8c3_direct_kernel<false><<<grid, kConsumerThreads, 0, st>>>(pe, pf, g, lines, src, dst, f, frame_bytes);
     }
     ctx->launches++;
     CC_CUDA(cudaGetLastError());

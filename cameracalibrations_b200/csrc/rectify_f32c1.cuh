@@ -107,36 +107,7 @@ rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_c
         __stcs(o, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b, fill));
 }
 
-// ---- staged kernel -------------------------------------------------------------------------
-// Persistent CTAs fed from a global ticket counter.  A work unit is one tile (strip x, tile y,
-// frame z), numbered x fastest, and units are handed out in that order to whichever CTA has a
-// free stage: at any instant the device works on a window of consecutive units, so tiles that
-// share source lines (the halos of neighbouring strips) are fetched within microseconds of each
-// other and the second fetch hits L2.  Static schedules (long private walks, round-robin) let
-// the CTAs drift apart and were measured to read 1.5x the frame from DRAM
-// (profiles/r1_rectify.md).
-//
-// Producer warp, per unit: take a ticket (one ticket ahead, so the atomic's latency is hidden),
-// decode it, read the tile header and the q2 terms from the plan, wait for a free stage, publish
-// {position, header, q2} in the stage's slot and issue ONE cp.async.bulk.tensor.  A ticket past
-// the last unit is published as a stop marker.  The last producer to leave resets the counter.
-__device__ __forceinline__ void ring_init(SmemRing* ring, int stages) {
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(&ring->full[s], 1);
-            mbar_init(&ring->empty[s], kWarps);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
-    uint32_t u = 0;
-    if (lane_id == 0) u = atomicAdd(&sched->next, 1u);
-    return __shfl_sync(0xffffffffu, u, 0);
-}
-
+// ---- staged kernel (persistent; scheduling and producer: rectify_ring.cuh) ------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
@@ -156,54 +127,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        if (lane_id == 0) tma_prefetch_desc(&tmap);
-        int s = 0;
-        uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
-        uint32_t u_next = take_ticket(sched, lane_id);
-        for (;;) {
-            const uint32_t u = u_next;
-            const bool live = u < cfg.units;
-            int x = 0, y = 0, z = 0;
-            uint32_t hword = 0;
-            [[maybe_unused]] double q2a = 0, q2b = 0;
-            if (live) {
-                x = (int)(u % (uint32_t)cfg.strips);
-                const uint32_t r = u / (uint32_t)cfg.strips;
-                y = (int)(r % (uint32_t)cfg.ntiles2);
-                z = (int)(r / (uint32_t)cfg.ntiles2);
-                const uint32_t* hp = reinterpret_cast<const uint32_t*>(plan + x * cfg.ntiles2 + y);
-                if (lane_id < 12) hword = __ldg(hp + lane_id);        // the 48-byte header, one word per lane
-                if (EXACT) {
-                    const int b = y * TL + lane_id;
-                    q2a = __ldg(q2tab + min(b, g.sz2 - 1));
-                    if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
-                }
-                u_next = take_ticket(sched, lane_id);
-            }
-            mbar_wait<kProducerSleep>(&ring.empty[s], phase);
-            if (!live) {
-                if (lane_id == 0) { ring.pos[s] = make_int4(0, 0, -1, 0); mbar_arrive(&ring.full[s]); }
-                break;
-            }
-            if (lane_id < 12) reinterpret_cast<uint32_t*>(&ring.hdr[s])[lane_id] = hword;
-            if (lane_id == 12) ring.pos[s] = make_int4(x, y, z, 0);
-            if (EXACT) {
-                if (lane_id < TL) ring.q2[s][lane_id] = q2a;
-                if (TL > 32) ring.q2[s][lane_id + 32] = q2b;
-            }
-            const int x0 = __shfl_sync(0xffffffffu, (int)hword, 8), y0 = __shfl_sync(0xffffffffu, (int)hword, 9);
-            __syncwarp();
-            if (lane_id == 0) {
-                mbar_arrive_expect_tx(&ring.full[s], (uint32_t)cfg.box_bytes);
-                tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, &tmap, &ring.full[s], x0, y0, z);
-            }
-            if (++s == cfg.stages) { s = 0; phase ^= 1; }
-        }
-        // every producer has taken its last ticket before it counts itself out
-        if (lane_id == 0 && atomicAdd(&sched->done, 1u) == gridDim.x - 1) {
-            sched->next = 0;
-            sched->done = 0;
-        }
+        producer_loop<EXACT, TL, 1>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 
