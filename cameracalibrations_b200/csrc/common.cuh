@@ -44,7 +44,7 @@ struct cc_ctx {
     double* jtj_scratch;
     size_t jtj_scratch_elems;
     // host pipeline: NSLOT streams with device staging buffers
-    static const int NSLOT = 3;
+    static const int NSLOT = 4;
     cudaStream_t pipe_stream[NSLOT];
     void* pipe_in[NSLOT];
     void* pipe_out[NSLOT];
