@@ -285,6 +285,55 @@ def test_rectify_edge_rule(cc):
     assert out[0, 0] == img[0, 0, 0] and out[0, 1] == 0.5 * (img[0, 0, 0] + img[0, 0, 1])
 
 
+def test_rectify_u8c3_exact_ties_take_the_fp64_blend(cc):
+    """The exact u8 kernel blends in FP32 and certifies the rounding; values within 6.5e-5 of a
+    rounding boundary are re-blended in FP64.  Half-integer sample positions make every weight
+    exactly 0.5, so a large share of the blended values are exact .5 / .25 / .75 ties or
+    near-ties: the output must still be the oracle's (round-half-even of the FP64 blend)."""
+    intr = (1.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+    view = ((0.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+    c = _calib(cc, intr, [view])
+    ch = oc.chain(intr, *view)
+    rng = np.random.default_rng(21)
+    sz = (256, 192)                                    # 256 * 3 bytes: TMA-addressable pitch
+    f8 = rng.integers(0, 256, (2, sz[1], sz[0], 3), dtype=np.uint8)
+    for ratio, axs in ((2.0, (2, 2)), (2.0, (3, 2)), (4.0, (5, 7)), (1.0, (1, 1))):
+        ref = oc.rectify_u8c3(ch, 1.0 / ratio, axs, f8, fill=(9, 8, 7))
+        for gather in ("tma", "direct"):
+            got = cc.warp(c, 0, _dev(f8), ratio, axs, fill=(9, 8, 7), gather=gather).cpu().numpy()
+            assert np.array_equal(got, ref), (ratio, axs, gather)
+        assert (ref != np.array([9, 8, 7], dtype=np.uint8)).any()
+
+
+def test_rectify_plan_cache_many_parameter_sets(cc):
+    """More parameter sets than the context caches tile plans for (8), revisited in a different
+    order and on two streams: every call must match the oracle (plans are keyed by calibration,
+    ratio, axes and frame geometry; an evicted plan is rebuilt)."""
+    sz = (128, 96)
+    intr = camera_for(sz)
+    rng = np.random.default_rng(3)
+    frames = rng.random((2, sz[1], sz[0]), dtype=np.float32)
+    fd = _dev(frames)
+    cases = []
+    for i in range(11):
+        view = ((0.05 + 0.01 * i, -0.04, 0.02 * (i % 3)), (-9.3 + 0.2 * i, -6.4, 30.0 + i))
+        ch, ip, ratio, axs = _rect_case(intr, sz, view=view)
+        cases.append((view, ch, ratio, axs))
+    c = _calib(cc, intr, [v for v, _, _, _ in cases])
+    refs = [oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-3.0) for _, ch, ratio, axs in cases]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for order in (range(11), reversed(range(11)), (0, 5, 0, 10, 5, 0)):
+        for i in order:
+            _, ch, ratio, axs = cases[i]
+            got = cc.warp(c, i, fd, ratio, axs, fill=-3.0).cpu().numpy()
+            assert np.array_equal(got, refs[i]), i
+            with torch.cuda.stream(side):
+                got2 = cc.warp(c, i, fd, ratio, axs, fill=-3.0, coord="f64")
+            side.synchronize()
+            assert np.array_equal(got2.cpu().numpy(), refs[i]), i
+
+
 @pytest.mark.parametrize("intr,sz", [(C2_INTR, (1080, 1920)), (C3_INTR, (2160, 3840))])
 def test_rectify_f32_coords_within_1e3_px(cc, intr, sz):
     """FP32 fast path: warp a row-ramp and a column-ramp; bilinear interpolation reproduces a
