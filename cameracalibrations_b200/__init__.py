@@ -8,7 +8,8 @@ reference's Julia interface over that ABI.  No CPU fallback exists.
 from ._lib import CamcalError, Context, context, device_count, LIB_PATH, EXPORTS
 from .calibration import (Calibration, rectification, get_ratio, get_axes, image_transformations,
                           warp, rectify_map, reproj_jtj, calculate_errors, save, load, views_tensor)
-from .fit import fit, detect_fit
+from .fit import fit, detect_fit, fit_model
+from .lm import lm_fit, lm_fit_host, initial_guess
 from .shard import shard_range, shard_frames
 
 RowCol = "SVector{2}: (row, col) -- arrays of shape (..., 2)"
@@ -17,4 +18,4 @@ XYZ = "SVector{3}: (x, y, z) -- arrays of shape (..., 3)"
 __all__ = ["Calibration", "rectification", "fit", "detect_fit", "get_ratio", "get_axes",
            "image_transformations", "warp", "rectify_map", "reproj_jtj", "calculate_errors", "save",
            "load", "views_tensor", "shard_range", "shard_frames", "CamcalError", "Context", "context",
-           "device_count", "RowCol", "XYZ"]
+           "device_count", "RowCol", "XYZ", "lm_fit", "lm_fit_host", "initial_guess", "fit_model"]

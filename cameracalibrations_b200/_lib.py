@@ -29,6 +29,9 @@ GATHER_TMA = 32
 
 PER_VIEW = 66
 SHARED = 21
+LM_YZ = 30
+LM_SCHUR = 21
+LM_DELTA = 8
 
 
 class CamcalError(RuntimeError):
@@ -88,6 +91,9 @@ _SIGS = {
     "cc_reproj_jtj_f64": (_i, [_vp, _pI, _d, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "cc_reproj_jtj_f64_host": (_i, [_vp, _pI, _d, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "cc_calculate_errors_f64": (_i, [_vp, _pI, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "cc_lm_schur_f64": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "cc_lm_update_f64": (_i, [_vp, _vp, _vp, _d, _u, _vp, _vp, _i, _vp, _vp, _vp]),
+    "cc_lm_fit_f64_host": (_i, [_vp, _pI, _d, _u, _vp, _i, _vp, _vp, _i, _i, _d, C.POINTER(_d), C.POINTER(_i)]),
 }
 
 EXPORTS = tuple(_SIGS)

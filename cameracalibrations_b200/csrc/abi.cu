@@ -45,6 +45,11 @@ int launch_reproj_jtj(cc_ctx*, const cc_intr*, double, const cc_view*, int, cons
                       const double*, int, double*, double*, cudaStream_t);
 int launch_calc_errors(cc_ctx*, const cc_intr*, const cc_view*, int, const double*, const double*,
                        int, int, const double*, const double*, int, double*, cudaStream_t);
+int launch_lm_schur(cc_ctx*, const double*, int, double, double*, double*, cudaStream_t);
+int lm_fit_host(cc_ctx*, cc_intr*, double, unsigned, cc_view*, int, const double*, const double*, int, int, double,
+                double*, int*);
+int launch_lm_update(cc_ctx*, const double*, const double*, double, unsigned, const double*, const cc_view*,
+                     int, cc_view*, double*, cudaStream_t);
 
 static int check_params(const cc_ctx* ctx, const cc_intr* intr, const cc_view* view) {
     CC_REQUIRE(ctx != nullptr, "ctx is NULL");
@@ -528,6 +533,46 @@ int cc_calculate_errors_f64(cc_ctx* ctx, const cc_intr* intr, const cc_view* vie
     if (rc) return rc;
     return launch_calc_errors(ctx, intr, views, nviews, obj, img, n1, n2, inv_rows, inv_cols,
                               inverse_samples, sums, (cudaStream_t)stream);
+}
+
+// ---- Levenberg-Marquardt step -----------------------------------------------------
+int cc_lm_schur_f64(cc_ctx* ctx, const double* per_view, int nviews, double lambda, double* yz,
+                    double* schur, void* stream) {
+    CC_REQUIRE(ctx && schur, "NULL argument");
+    CC_REQUIRE(nviews >= 0, "bad sizes");
+    CC_REQUIRE(nviews == 0 || (per_view && yz), "NULL device pointer");
+    CC_REQUIRE(lambda >= 0.0 && lambda == lambda, "lambda must be non-negative");
+    int rc = enter(ctx);
+    if (rc) return rc;
+    return launch_lm_schur(ctx, per_view, nviews, lambda, yz, schur, (cudaStream_t)stream);
+}
+
+int cc_lm_update_f64(cc_ctx* ctx, const double* shared, const double* schur, double lambda,
+                     unsigned free_mask, const double* yz, const cc_view* views_in, int nviews,
+                     cc_view* views_out, double* delta, void* stream) {
+    CC_REQUIRE(ctx && shared && schur && delta, "NULL argument");
+    CC_REQUIRE(nviews >= 0, "bad sizes");
+    CC_REQUIRE(nviews == 0 || (yz && views_in && views_out), "NULL device pointer");
+    CC_REQUIRE(lambda >= 0.0 && lambda == lambda, "lambda must be non-negative");
+    CC_REQUIRE(free_mask != 0u && free_mask < 16u, "free_mask selects among the 4 shared parameters");
+    int rc = enter(ctx);
+    if (rc) return rc;
+    return launch_lm_update(ctx, shared, schur, lambda, free_mask, yz, views_in, nviews, views_out, delta,
+                            (cudaStream_t)stream);
+}
+
+int cc_lm_fit_f64_host(cc_ctx* ctx, cc_intr* intr, double aspect, unsigned free_mask, cc_view* views,
+                       int nviews, const double* obj, const double* img, int ncorners, int max_iter,
+                       double eps, double* rms, int* iterations) {
+    CC_REQUIRE(ctx && intr && views && obj && img, "NULL argument");
+    CC_REQUIRE(nviews > 0 && ncorners > 0, "bad sizes");
+    CC_REQUIRE(free_mask != 0u && free_mask < 16u, "free_mask selects among the 4 shared parameters");
+    CC_REQUIRE(max_iter >= 0 && eps >= 0.0, "bad stopping rule");
+    CC_REQUIRE(aspect > 0.0 && intr->fcol != 0.0 && intr->checker_size != 0.0, "bad starting intrinsics");
+    int rc = enter(ctx);
+    if (rc) return rc;
+    return lm_fit_host(ctx, intr, aspect, free_mask, views, nviews, obj, img, ncorners, max_iter, eps, rms,
+                       iterations);
 }
 
 }  // extern "C"

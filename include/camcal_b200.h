@@ -188,6 +188,37 @@ int cc_calculate_errors_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *vie
                             const double *inv_rows, const double *inv_cols,
                             int inverse_samples, double *sums, void *stream);
 
+/* ---- one Levenberg-Marquardt step on those blocks (the solve OpenCV.calibrateCamera runs
+ *      inside the reference's fit, src/detect_fit.jl:47; flags :40; CRITERIA
+ *      src/CameraCalibrations.jl:16).  Arrowhead system, Schur complement on the 4 shared
+ *      parameters; Marquardt damping  diag *= (1 + lambda).
+ *      phase 1  cc_lm_schur_f64 : per view  Y = A'^-1 B (6x4), z = A'^-1 g (6)  -> yz (device,
+ *               nviews x 30); schur (device, CC_LM_SCHUR = 21): [S 4x4 | s 4 | #views whose
+ *               6x6 block was not positive definite], summed over THIS device's views in a fixed
+ *               order.  All-reduce schur across ranks when views are sharded (host layer).
+ *      phase 2  cc_lm_update_f64: (C' - S) di = -(gi - s);  de = -(z + Y di);
+ *               views_out = views_in + de;  delta (device, CC_LM_DELTA = 8):
+ *               [di 4 | sum |de|^2 | sum |rvec,tvec|^2 | 1.0 if the 4x4 solve succeeded | 0].
+ *               free_mask: bit j set = shared parameter j (f, crow, ccol, k) is free
+ *               (CALIB_FIX_K1 clears bit 3).  `shared` is the all-reduced block of cc_reproj_jtj. */
+#define CC_LM_YZ 30
+#define CC_LM_SCHUR 21
+#define CC_LM_DELTA 8
+int cc_lm_schur_f64(cc_ctx *ctx, const double *per_view, int nviews, double lambda, double *yz,
+                    double *schur, void *stream);
+int cc_lm_update_f64(cc_ctx *ctx, const double *shared, const double *schur, double lambda,
+                     unsigned free_mask, const double *yz, const cc_view *views_in, int nviews,
+                     cc_view *views_out, double *delta, void *stream);
+/* The whole fit on one device with HOST arrays: the call that replaces
+ * OpenCV.calibrateCamera(objectPoints, imagePoints, ..., flags, CRITERIA) of
+ * src/detect_fit.jl:47.  intr/views: starting values in, fitted values out (frow = aspect*fcol is
+ * kept, CALIB_FIX_ASPECT_RATIO); lambda schedule of CvLevMarq (1e-3, /10 accepted, *10 rejected);
+ * stops after max_iter steps or when |step| < eps * |parameters| (CRITERIA: 30, 1e-3).
+ * rms = sqrt(sum |residual|^2 / (nviews * ncorners)), what calibrateCamera returns. */
+int cc_lm_fit_f64_host(cc_ctx *ctx, cc_intr *intr, double aspect, unsigned free_mask,
+                       cc_view *views, int nviews, const double *obj, const double *img,
+                       int ncorners, int max_iter, double eps, double *rms, int *iterations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,4 +146,24 @@ function reproj_jtj(c::Calibration, aspect::Float64, objpoints::Matrix{Float64},
     per_view, shared
 end
 
+# ---- the fit itself: replaces the OpenCV.calibrateCamera call of src/detect_fit.jl:47 --------
+# Starting values as calibrateCamera derives them (principal point at the image centre, focal
+# length from the homographies: OpenCV.initCameraMatrix2D; per-view pose: OpenCV.solvePnP), then ONE
+# ccall runs the whole Levenberg-Marquardt loop on the device (same flags :40, same CRITERIA).
+# `k`, `Rs`, `ts`, `frow`, ... come back in the NamedTuple fit_model returns today (:60).
+function lm_fit!(intr::Base.RefValue{CcIntr}, views::Vector{CcView}, aspect::Float64, with_distortion::Bool,
+                 objpoints::Matrix{Float64},           # 3 x ncorners, board units
+                 imgpoints::Array{Float64,3};          # 2 x ncorners x nviews, (row, col)
+                 max_iter::Int = 30, eps::Float64 = 1e-3)
+    nc, nv = size(imgpoints, 2), size(imgpoints, 3)
+    rms, its = Ref{Cdouble}(0), Ref{Cint}(0)
+    check(ccall((:cc_lm_fit_f64_host, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Cdouble, Cuint, Ptr{CcView}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint,
+                 Cint, Cdouble, Ref{Cdouble}, Ref{Cint}),
+                context().handle, intr, aspect, with_distortion ? 0x0f : 0x07, views, nv, objpoints, imgpoints,
+                nc, max_iter, eps, rms, its))
+    (; k = intr[].k, Rs = [collect(v.rvec) for v in views], ts = [collect(v.tvec) for v in views],
+       frow = intr[].frow, fcol = intr[].fcol, crow = intr[].crow, ccol = intr[].ccol, rms = rms[], iterations = its[])
+end
+
 end # module

@@ -1,0 +1,190 @@
+"""Levenberg-Marquardt fit (cameracalibrations_b200/lm.py + csrc/lm.cu): the solve the reference
+delegates to OpenCV.calibrateCamera (src/detect_fit.jl:47).  Checked against
+  * a dense numpy solve of the same damped normal equations built from the ORACLE's blocks,
+  * the cv2.calibrateCamera result stored in tests/golden/example_fit.json (same flags as
+    src/detect_fit.jl:40; cv2 stops at the reference's CRITERIA, the LM here may go further,
+    so its RMS must be <= cv2's).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+
+
+def _dense_step(pv, sh, lam, views, mask=0b1111):
+    """(A + lam diag A) delta = -g on the full arrowhead matrix, numpy"""
+    nv = len(views)
+    n = 6 * nv + 4
+    H, g = np.zeros((n, n)), np.zeros(n)
+    for v in range(nv):
+        s = slice(6 * v, 6 * v + 6)
+        H[s, s] = pv[v, :36].reshape(6, 6)
+        H[s, 6 * nv:] = pv[v, 36:60].reshape(6, 4)
+        H[6 * nv:, s] = pv[v, 36:60].reshape(6, 4).T
+        g[s] = pv[v, 60:66]
+    H[6 * nv:, 6 * nv:] = sh[:16].reshape(4, 4)
+    g[6 * nv:] = sh[16:20]
+    H[np.diag_indices(n)] *= 1.0 + lam
+    for a in range(4):
+        if not (mask >> a) & 1:
+            j = 6 * nv + a
+            H[j, :] = 0; H[:, j] = 0; H[j, j] = 1; g[j] = 0
+    d = np.linalg.solve(H, -g)
+    return d[6 * nv:], np.asarray(views) + d[:6 * nv].reshape(nv, 6)
+
+
+# ------------------------------------------------------------------ host logic (CPU)
+def test_initial_guess_close_to_cv2(example_fit):
+    from cameracalibrations_b200 import lm
+    intr0, views0 = lm.initial_guess(example_fit["obj_np"], example_fit["corners_np"], example_fit["sz"], 1.0)
+    cv = example_fit["intr_tuple"]
+    assert abs(intr0[0] - cv[0]) / cv[0] < 0.02 and intr0[0] == intr0[1]
+    assert intr0[2:4] == ((example_fit["sz"][0] - 1) / 2.0, (example_fit["sz"][1] - 1) / 2.0) and intr0[4] == 0.0
+    for v0, (rv, tv) in zip(views0, example_fit["view_list"]):
+        assert np.max(np.abs(v0[:3] - rv)) < 0.05 and np.max(np.abs(v0[3:] - tv)) < 0.25
+    # reprojection error of the starting point, through the oracle: a usable start (a few px)
+    _, sh, _ = oc.reproj_jtj(tuple(intr0) + (1.0,), 1.0, [(v[:3], v[3:]) for v in views0],
+                             example_fit["obj_np"], example_fit["corners_np"])
+    assert np.sqrt(sh[20] / example_fit["corners_np"][..., 0].size) < 3.0
+
+
+def test_rodrigues_inverse_round_trip():
+    from cameracalibrations_b200 import lm
+    from oracle import oracle_np as on
+    rng = np.random.default_rng(5)
+    for rv in list(rng.normal(0, 1.0, (50, 3))) + [np.zeros(3), np.array([np.pi - 1e-9, 0, 0]), np.array([1e-14, 0, 0])]:
+        back = lm._rodrigues_inv(on.rodrigues(rv))
+        assert np.allclose(on.rodrigues(back), on.rodrigues(rv), atol=1e-9)
+
+
+# ------------------------------------------------------------------ device (GPU)
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def cc():
+    import cameracalibrations_b200 as m
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m.context(0)
+    return m
+
+
+def _c5(nviews, seed=7):
+    rng = np.random.default_rng(seed)
+    n1, n2 = 20, 14
+    intr = (2800.0, 2800.0, 1080.0, 1920.0, -0.12, 1.0)
+    obj = np.array([[a, b, 0.0] for b in range(n2) for a in range(n1)], dtype=np.float64)
+    rv = rng.normal(0, 0.3, (nviews, 3))
+    tv = np.array([-10.0, -7.0, 40.0]) + rng.normal(0, 2.0, (nviews, 3))
+    img = np.empty((nviews, n1 * n2, 2))
+    for i in range(nviews):
+        img[i, :, 0], img[i, :, 1] = oc.world2img(oc.chain(intr, rv[i], tv[i]), obj)
+    return intr, np.concatenate([rv, tv], 1), obj, img, rng
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lam,mask", [(1e-3, 0b1111), (10.0, 0b1111), (0.0, 0b0111), (1e-6, 0b0111)])
+def test_lm_step_matches_dense_solve(cc, lam, mask):
+    from cameracalibrations_b200 import lm
+    intr, views, obj, img, rng = _c5(37)
+    img = img + rng.normal(0, 0.25, img.shape)
+    start = views + rng.normal(0, 1e-3, views.shape)                # off the optimum: non-zero gradient
+    pv_o, sh_o, _ = oc.reproj_jtj(intr, 1.0, [(v[:3], v[3:]) for v in start], obj, img)
+    di_ref, cand_ref = _dense_step(pv_o, sh_o, lam, start, mask)
+    dv = torch.device("cuda")
+    pv, sh = cc.reproj_jtj(intr, 1.0, torch.from_numpy(start).to(dv), torch.from_numpy(obj).to(dv), torch.from_numpy(img).to(dv))
+    yz, schur = lm.lm_schur(pv, lam)
+    cand, delta = lm.lm_update(sh, schur, lam, mask, yz, torch.from_numpy(start).to(dv))
+    d = delta.cpu().numpy()
+    assert schur[20].item() == 0.0 and d[6] == 1.0
+    scale = np.abs(di_ref).max()
+    assert np.max(np.abs(d[:4] - di_ref)) <= 1e-7 * scale + 1e-12
+    if not mask & 0b1000:
+        assert d[3] == 0.0
+    assert np.max(np.abs(cand.cpu().numpy() - cand_ref)) <= 1e-7 * np.abs(cand_ref - start).max() + 1e-12
+    assert np.isclose(d[4], np.sum((cand_ref - start) ** 2), rtol=1e-6)
+    assert np.isclose(d[5], np.sum(start ** 2), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_lm_fit_example_reaches_cv2_optimum(cc, example_fit):
+    """From the homography start to (at least) cv2.calibrateCamera's optimum on test/example."""
+    from cameracalibrations_b200 import lm
+    obj, imgs = example_fit["obj_np"], example_fit["corners_np"]
+    intr0, views0 = lm.initial_guess(obj, imgs, example_fit["sz"], 1.0)
+    hist = []
+    r = lm.lm_fit(intr0, views0, obj, imgs, history=hist)            # CRITERIA defaults (30, 1e-3)
+    assert r["iterations"] <= 30 and r["accepted"] >= 2
+    assert r["rms"] <= example_fit["cv2_rms"] + 1e-6
+    tight = lm.lm_fit(intr0, views0, obj, imgs, max_iter=60, eps=1e-10)
+    assert tight["rms"] <= example_fit["cv2_rms"] and tight["rms"] <= r["rms"] + 1e-12
+    cv = example_fit["intr_tuple"]
+    assert abs(tight["intr"][0] - cv[0]) / cv[0] < 1e-4 and tight["intr"][0] == tight["intr"][1]
+    assert abs(tight["intr"][2] - cv[2]) < 0.05 and abs(tight["intr"][3] - cv[3]) < 0.05
+    assert abs(tight["intr"][4] - cv[4]) < 1e-3
+    for v, (rv, tv) in zip(tight["views"], example_fit["view_list"]):
+        assert np.max(np.abs(v[:3] - rv)) < 1e-3 and np.max(np.abs(v[3:] - tv)) < 5e-3
+    # at the optimum the gradient vanishes (oracle's blocks at the fitted parameters)
+    pv, sh, _ = oc.reproj_jtj(tuple(tight["intr"]) + (1.0,), 1.0, [(v[:3], v[3:]) for v in tight["views"]], obj, imgs)
+    pv0, sh0, _ = oc.reproj_jtj(tuple(intr0) + (1.0,), 1.0, [(v[:3], v[3:]) for v in views0], obj, imgs)
+    assert np.abs(sh[16:20]).max() <= 1e-6 * np.abs(sh0[16:20]).max()
+    assert np.abs(pv[:, 60:]).max() <= 1e-6 * np.abs(pv0[:, 60:]).max()
+    # the fitted object is the reference's calibration object: errors below the reference's bounds
+    c = cc.Calibration.from_fit([v[:3] for v in tight["views"]], [v[3:] for v in tight["views"]], *tight["intr"][:4],
+                                1.0, tight["intr"][4], example_fit["files"])
+    eps = cc.calculate_errors(c, imgs, obj, 1.0, example_fit["sz"], example_fit["files"], example_fit["n_corners"],
+                              rng=np.random.default_rng(1))
+    assert all(eps[k] < 1.0 for k in ("reprojection", "projection", "distance", "inverse"))   # test/runtests.jl:76
+
+
+@pytest.mark.gpu
+def test_lm_fit_host_entry_point_is_the_same_fit(cc, example_fit):
+    """cc_lm_fit_f64_host (one C-ABI call, host arrays) runs the same loop as lm.lm_fit."""
+    from cameracalibrations_b200 import lm
+    obj, imgs = example_fit["obj_np"], example_fit["corners_np"]
+    intr0, views0 = lm.initial_guess(obj, imgs, example_fit["sz"], 1.0)
+    a = lm.lm_fit(intr0, views0, obj, imgs)
+    b = lm.lm_fit_host(intr0, views0, obj, imgs)
+    assert a["iterations"] == b["iterations"]
+    assert np.array_equal(np.asarray(a["intr"]), np.asarray(b["intr"])) and np.array_equal(a["views"], b["views"])
+    assert a["rms"] == b["rms"] and b["rms"] <= example_fit["cv2_rms"] + 1e-6
+    # bad arguments are status codes
+    with pytest.raises(cc.CamcalError):
+        lm.lm_fit_host(intr0, views0, obj, imgs, max_iter=-1)
+
+
+@pytest.mark.gpu
+def test_fit_model_device_solver_vs_opencv(cc, example_fit):
+    """fit_model (src/detect_fit.jl:27-61) with solver="b200" against solver="opencv" (cv2 here,
+    OpenCV.jl in the reference) on the golden corners of test/example: same model, same optimum."""
+    pytest.importorskip("cv2")
+    obj, imgs, sz = example_fit["obj_np"], example_fit["corners_np"], tuple(example_fit["sz"])
+    a = cc.fit_model(sz, obj, imgs, example_fit["n_corners"], solver="b200")
+    b = cc.fit_model(sz, obj, imgs, example_fit["n_corners"], solver="opencv")
+    assert a["rms"] <= b["rms"] + 1e-6                     # cv2 works on float32 copies of the corners
+    assert abs(a["frow"] - b["frow"]) / b["frow"] < 1e-3 and a["frow"] == a["fcol"]
+    assert abs(a["crow"] - b["crow"]) < 0.1 and abs(a["ccol"] - b["ccol"]) < 0.1 and abs(a["k"] - b["k"]) < 2e-3
+    for ra, rb, ta, tb in zip(a["Rs"], b["Rs"], a["ts"], b["ts"]):
+        assert np.max(np.abs(ra - rb)) < 2e-3 and np.max(np.abs(ta - tb)) < 1e-2
+    # without distortion too (CALIB_FIX_K1)
+    a0 = cc.fit_model(sz, obj, imgs, example_fit["n_corners"], with_distortion=False, solver="b200")
+    b0 = cc.fit_model(sz, obj, imgs, example_fit["n_corners"], with_distortion=False, solver="opencv")
+    assert a0["k"] == 0.0 and b0["k"] == 0.0 and a0["rms"] <= b0["rms"] + 1e-6
+
+
+@pytest.mark.gpu
+def test_lm_fit_without_distortion_and_many_views(cc):
+    """CALIB_FIX_K1 (with_distortion == false) keeps k at 0; 500 noisy synthetic views converge to the
+    generating camera."""
+    from cameracalibrations_b200 import lm
+    intr, views, obj, img, rng = _c5(500, seed=11)
+    intr = intr[:4] + (0.0, 1.0)
+    for i in range(len(views)):
+        img[i, :, 0], img[i, :, 1] = oc.world2img(oc.chain(intr, views[i, :3], views[i, 3:]), obj)
+    noisy = img + rng.normal(0, 0.1, img.shape)
+    intr0, views0 = lm.initial_guess(obj, noisy, (2160, 3840), 1.0)
+    r = lm.lm_fit(intr0, views0, obj, noisy, with_distortion=False, max_iter=40, eps=1e-9)
+    assert r["intr"][4] == 0.0
+    assert abs(r["rms"] - 0.1 * np.sqrt(2)) < 0.005          # noise floor: sqrt(2) sigma per point
+    assert abs(r["intr"][0] - 2800.0) < 1.0 and abs(r["intr"][2] - 1080.0) < 1.0 and abs(r["intr"][3] - 1920.0) < 1.0
+    assert np.max(np.abs(r["views"] - views)) < 0.05
