@@ -93,3 +93,72 @@ def test_shard_range_properties():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# LM step with views sharded over ranks: per-rank Schur shares (what lm_schur_kernel emits),
+# all-reduced, must give the step of the unsharded dense system (tests/test_lm.py::_dense_step).
+# The per-rank arithmetic is numpy here (checker), the exchange is the real collective.
+def _schur_share(pv, lam):
+    S, s, Y, Z = np.zeros((4, 4)), np.zeros(4), [], []
+    for b in pv:
+        A = b[:36].reshape(6, 6).copy()
+        A[np.diag_indices(6)] *= 1.0 + lam
+        B, g = b[36:60].reshape(6, 4), b[60:66]
+        y, z = np.linalg.solve(A, B), np.linalg.solve(A, g)
+        S += B.T @ y
+        s += B.T @ z
+        Y.append(y)
+        Z.append(z)
+    return np.concatenate([S.ravel(), s, [0.0]]), Y, Z
+
+
+def _lm_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle_c as oc
+    from cameracalibrations_b200.shard import shard_range
+    intr, views, obj, img = _case(nviews=9)
+    lam = 1e-3
+    lo, hi = shard_range(len(views), rank, world)
+    pv, sh, _ = oc.reproj_jtj(intr, 1.0, views[lo:hi], obj, img[lo:hi])
+    sh_t = torch.from_numpy(sh.copy())
+    dist.all_reduce(sh_t)                                   # reproj_jtj's exchange
+    share, Y, Z = _schur_share(pv, lam)
+    sc_t = torch.from_numpy(share.copy())
+    dist.all_reduce(sc_t)                                   # lm_fit's exchange after cc_lm_schur_f64
+    sh_all, sc = sh_t.numpy(), sc_t.numpy()
+    M = sh_all[:16].reshape(4, 4) - sc[:16].reshape(4, 4)
+    M[np.diag_indices(4)] += lam * np.diag(sh_all[:16].reshape(4, 4))
+    di = np.linalg.solve(M, -(sh_all[16:20] - sc[16:20]))   # cc_lm_update_f64, every rank the same
+    de = np.array([-(Z[i] + Y[i] @ di) for i in range(hi - lo)]).reshape(hi - lo, 6)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, di, de))
+    if rank == 0:
+        out.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_lm_step_equals_unsharded_dense_solve():
+    from oracle import oracle_c as oc
+    from test_lm import _dense_step
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lm_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    intr, views, obj, img = _case(nviews=9)
+    pv, sh, _ = oc.reproj_jtj(intr, 1.0, views, obj, img)
+    start = np.array([np.concatenate(v) for v in views])
+    di_ref, cand_ref = _dense_step(pv, sh, 1e-3, start)
+    assert np.array_equal(gathered[0][2], gathered[1][2])               # identical decision inputs
+    np.testing.assert_allclose(gathered[0][2], di_ref, rtol=1e-8, atol=1e-14)
+    de = np.concatenate([g[3] for g in gathered])
+    np.testing.assert_allclose(start + de, cand_ref, rtol=1e-9, atol=1e-12)
