@@ -405,6 +405,15 @@ def extras(cc, torch, dev, c2cal, args):
     ms = _time_ms(torch, lambda: cc.reproj_jtj(wl["intr"], 1.0, tv, to, ti), 20)
     ex["reproj_jtj_10k_views"] = {"views_per_s": nv / (ms * 1e-3), "ms": ms,
                                   "gb_per_s": 4936 * nv / (ms * 1e-3) / 1e9}
+    # one Levenberg-Marquardt step on those blocks: Schur elimination + update (csrc/lm.cu)
+    from cameracalibrations_b200 import lm
+    pv, sh = cc.reproj_jtj(wl["intr"], 1.0, tv, to, ti)
+
+    def lm_step():
+        yz, schur = lm.lm_schur(pv, 1e-3)
+        lm.lm_update(sh, schur, 1e-3, lm.FREE_ALL, yz, tv)
+    ms = _time_ms(torch, lm_step, 20)
+    ex["lm_step_10k_views"] = {"views_per_s": nv / (ms * 1e-3), "ms": ms}
     return ex
 
 
