@@ -153,6 +153,31 @@ def test_f32_fast_path_round_trip(cc):
     assert np.max(np.abs(c32.cpu().numpy() - c64)) <= TOL32_PX
 
 
+@pytest.mark.parametrize("k", [0.0, 0.056417832172007555, 0.9, 1.5, 3.0, -0.2])
+def test_f32_inverse_distortion_fixed_and_generic_schedules(cc, k):
+    """FP32 pixel->world over lenses whose c = k r^2 stays inside the fixed-schedule range
+    [-0.12, 1] (k <= 1.5 on this frame), straddles its upper end (k = 3) or its lower end (k = -0.2:
+    c down to -0.124): the FP64 oracle maps the FP32 world point back within 1e-3 px."""
+    intr = C3_INTR[:4] + (k, 1.0)
+    c = _calib(cc, intr, [SYN_VIEW])
+    ch = oc.chain(intr, *SYN_VIEW)
+    rng = np.random.default_rng(17)
+    n = 200_003
+    row = rng.uniform(0, 2160, n).astype(np.float32)
+    col = rng.uniform(0, 3840, n).astype(np.float32)
+    x, y, z = c.img2world(_dev(row), _dev(col), 0)
+    r64, c64 = oc.world2img_soa(ch, x.cpu().numpy().astype(np.float64), y.cpu().numpy().astype(np.float64),
+                                z.cpu().numpy().astype(np.float64))
+    # the forward map amplifies an error of the root by its own slope: allow for it when k is large
+    slope = 1.0 + 3.0 * abs(k) * 0.62
+    assert np.max(np.maximum(np.abs(r64 - row), np.abs(c64 - col))) <= TOL32_PX * slope
+    # and the FP64 kernel (whose seed is the same FP32 schedule) stays at 1e-9
+    x64, y64, z64 = c.img2world(_dev(row.astype(np.float64)), _dev(col.astype(np.float64)), 0)
+    ox, oy, oz = oc.img2world_soa(ch, row.astype(np.float64), col.astype(np.float64))
+    scale = max(1.0, float(np.max(np.abs(ox))), float(np.max(np.abs(oy))))
+    assert np.max(np.abs(x64.cpu().numpy() - ox)) <= TOL64 * scale
+
+
 def test_host_entry_points_match_device(cc):
     c = _calib(cc, C2_INTR, [SYN_VIEW])
     rng = np.random.default_rng(3)
