@@ -209,6 +209,12 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                 for (int e = 0; e < KB; ++e) {
                     const uint32_t q = base + t2[e] * box_pitch_b + t1[e] * 4u;
                     const uint32_t q1 = q + box_pitch_b;
+#ifdef CAMCAL_CHECK_BOUNDS      // debug builds (profiles/mkvariant.sh chk "-DCAMCAL_CHECK_BOUNDS"): taps inside the stage
+                    {
+                        const uint32_t lo = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+                        if (q < lo || q1 + 8u > lo + (uint32_t)cfg.box_bytes || (q & 3u)) __trap();
+                    }
+#endif
                     a00[e] = lds_f32(q); a10[e] = lds_f32_off<4>(q);
                     a01[e] = lds_f32(q1); a11[e] = lds_f32_off<4>(q1);
                 }

@@ -319,6 +319,12 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 #pragma unroll
                 for (int e = 0; e < KB; ++e) {
                     const uint32_t o = base + t2[e] * box_pitch_b + t1[e] * 3u;
+#ifdef CAMCAL_CHECK_BOUNDS      // debug builds: the six tap bytes of both lines inside the stage
+                    {
+                        const uint32_t lo = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+                        if (o < lo || o + box_pitch_b + 6u > lo + (uint32_t)cfg.box_bytes) __trap();
+                    }
+#endif
                     const unsigned sel = sel6(o);              // box_pitch_b % 4 == 0: same for both lines
                     ta[e] = lds6(o, sel);
                     tb[e] = lds6(o + box_pitch_b, sel);
