@@ -358,6 +358,7 @@ int cc_rectify_f32c1(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doub
     if (rc) return rc;
     if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, frame_stride, nframes, ratio))) return rc;
     CC_REQUIRE(nframes == 0 || (src && dst), "NULL frame pointer");
+    CC_REQUIRE(nframes == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
     build_chain(intr, view, &ch);
@@ -373,6 +374,7 @@ int cc_rectify_u8c3(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doubl
     if (rc) return rc;
     if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, frame_stride, nframes, ratio))) return rc;
     CC_REQUIRE(nframes == 0 || (src && dst), "NULL frame pointer");
+    CC_REQUIRE(nframes == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
     CC_REQUIRE(fill != nullptr, "fill is NULL");
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
@@ -389,6 +391,7 @@ int cc_rectify_f32c1_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* view,
     if (rc) return rc;
     if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, frame_stride, nframes, ratio))) return rc;
     CC_REQUIRE(nframes == 0 || (src && dst), "NULL frame pointer");
+    CC_REQUIRE(nframes == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
     ChainD ch;
     build_chain(intr, view, &ch);
     return rectify_host<float>(
@@ -407,6 +410,7 @@ int cc_rectify_u8c3_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, 
     if (rc) return rc;
     if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, frame_stride, nframes, ratio))) return rc;
     CC_REQUIRE(nframes == 0 || (src && dst), "NULL frame pointer");
+    CC_REQUIRE(nframes == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
     CC_REQUIRE(fill != nullptr, "fill is NULL");
     ChainD ch;
     build_chain(intr, view, &ch);

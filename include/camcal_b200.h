@@ -18,6 +18,12 @@
  *    asynchronous on `stream` (a cudaStream_t passed as void*, NULL = default
  *    stream); `*_host` variants take HOST pointers, run a chunked
  *    H2D -> kernel -> D2H pipeline and return when the result is in host memory.
+ *  - a cc_ctx belongs to one device and is not internally locked: use one context per
+ *    host thread, or serialise the calls on it.  It owns the host pipeline's staging
+ *    buffers, the cached rectification tile plans (the 8 most recent calibration /
+ *    geometry sets) and the tile-scheduler counters; calls on different streams of the
+ *    same context may overlap on the device.
+ *  - rectification is out of place (src != dst).
  *  - point sets are SoA (one array per coordinate).  Pointers aligned to 16 bytes
  *    take the 128-bit vector path; unaligned pointers are accepted (scalar path).
  *  - frames are stored the way Julia stores `img[r, c]` (size (sz1, sz2)): pixel

@@ -204,6 +204,9 @@ def test_bad_arguments(cc):
     assert c2(np.array([[5.0, 6.0]])).shape == (1, 3)     # src/meta.jl:90-93
     with pytest.raises(cc.CamcalError):
         cc.warp(c, 0, np.zeros((1, 8, 8), np.float32), -1.0, (0, 0))
+    f = torch.zeros((1, 8, 8), device="cuda")
+    with pytest.raises(cc.CamcalError, match="in place"):
+        cc.warp(c, 0, f, 1.0, (0, 0), out=f)              # rectification is out of place
 
 
 # ------------------------------------------------------------------ rectification
