@@ -39,10 +39,14 @@ namespace cc {
 constexpr int kT = 32;                 // strip width along the first axis = lanes of a warp
 constexpr int kWarps = 4;              // consumer warps per CTA
 #ifndef CAMCAL_TL_F32
-#define CAMCAL_TL_F32 64
+#define CAMCAL_TL_F32 32
 #endif
 constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTLf / kWarps of them)
 constexpr int kTLmax = 64;
+#ifndef CAMCAL_FG_MAX
+#define CAMCAL_FG_MAX 16
+#endif
+constexpr int kFGmax = CAMCAL_FG_MAX;  // most frames one unit rectifies with one map
 #ifndef CAMCAL_TL_U8
 #define CAMCAL_TL_U8 64
 #endif
@@ -96,7 +100,8 @@ struct TileCfg {
     int box_bytes;         // bytes one TMA load delivers = stage stride (multiple of 128)
     // persistent f32c1 kernels: work units (strip x, tile y, frame z), x fastest
     int strips;            // tiles along the first axis
-    uint32_t units;        // strips * ntiles2 * nframes
+    uint32_t units;        // strips * ntiles2 * frame groups
+    int fg;                // frames per group: the tile's map is built once per group and reused
 };
 
 // f32c1: per-tile header precomputed on the host (RectPlan), read straight from global memory
@@ -419,8 +424,8 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     if (!enc) return false;
     RectPlan* plan = plan_get(ctx, ch, ratio, g, tw, tl, pxb, st);
     if (!plan || !plan->box_bytes) return false;
-    // measured (profiles/r1_rectify.md): occupancy beats ring depth
-    int stages = 2;
+    // measured (profiles/r1_rectify.md): occupancy beats ring depth; small boxes afford more stages
+    int stages = std::min(kMaxStages, std::max(2, 24576 / plan->box_bytes));
     if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
     while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 
@@ -487,17 +492,27 @@ static int persistent_grid(cc_ctx* ctx, K kernel, size_t smem, const TileCfg& cf
     if (const char* e = getenv("CAMCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // tuning knob
     *gsz = std::min<uint32_t>(cfg.units, (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1));
     if (getenv("CAMCAL_DEBUG"))
-        fprintf(stderr, "[camcal] staged: box %dx%d (%d B) stages %d units %u grid %u (%d/SM) smem %zu\n",
-                cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.units, *gsz, per_sm, smem);
+        fprintf(stderr, "[camcal] staged: box %dx%d (%d B) stages %d units %u (fg %d) grid %u (%d/SM) smem %zu\n",
+                cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.units, cfg.fg, *gsz, per_sm, smem);
     return CC_OK;
 }
 
-static int unit_cfg(TileCfg* cfg, int sz1, int sz2, int nframes, int tw, int tl) {
+// Frames per group.  The map of a tile (indices, weights) depends on the calibration only, so a
+// unit rectifies the same tile of `fg` consecutive frames and computes the map once.  Larger
+// groups amortise better; smaller ones leave more units for the tail of the ticket queue: keep
+// at least ~8 units per resident CTA slot.
+static int unit_cfg(cc_ctx* ctx, TileCfg* cfg, int sz1, int sz2, int nframes, int tw, int tl, int fg_max) {
     cfg->strips = (sz1 + tw - 1) / tw;
     cfg->ntiles2 = (sz2 + tl - 1) / tl;
-    CC_REQUIRE((unsigned long long)cfg->strips * cfg->ntiles2 * nframes < (1ull << 31),
-               "too many tiles in one call: split the batch");
-    cfg->units = (uint32_t)cfg->strips * (uint32_t)cfg->ntiles2 * (uint32_t)nframes;
+    const long long tiles = (long long)cfg->strips * cfg->ntiles2;
+    const long long want = (long long)ctx->sm_count * 6 * 8;
+    int fg = std::min(fg_max, nframes);
+    while (fg > 1 && tiles * ((nframes + fg - 1) / fg) < want) fg = (fg + 1) / 2;
+    if (const char* e = getenv("CAMCAL_FG")) fg = std::max(1, std::min(nframes, atoi(e)));   // tuning knob
+    cfg->fg = fg;
+    const long long groups = (nframes + fg - 1) / fg;
+    CC_REQUIRE(tiles * groups < (1ll << 31), "too many tiles in one call: split the batch");
+    cfg->units = (uint32_t)(tiles * groups);
     return CC_OK;
 }
 
@@ -529,7 +544,7 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     int rc = CC_OK;
     if (tma) {
-        if ((rc = unit_cfg(&cfg, sz1, sz2, nframes, kT * kWXf, kTLf))) return rc;
+        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT * kWXf, kTLf, kFGmax))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, &gsz)
@@ -578,7 +593,7 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     int rc = CC_OK;
     if (tma) {
-        if ((rc = unit_cfg(&cfg, sz1, sz2, nframes, kT, kTLu))) return rc;
+        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLu, 1))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, &gsz)

@@ -108,6 +108,19 @@ rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_c
 }
 
 // ---- staged kernel (persistent; scheduling and producer: rectify_ring.cuh) ------------------
+// The map of a tile -- tap address, weights, and whether the pixel is staged / fill / generic --
+// depends on the calibration only.  A unit is one tile of a GROUP of frames: the consumers build
+// the map once (pos.w set on the group's first frame), keep it in registers (8 pixels per lane),
+// and for every further frame only gather, blend and store.  Per frame and pixel that is 4 LDS,
+// the blend and one store; the coordinate chain (23 of the 31 FP64 instructions of the exact
+// variant) is paid once per group.
+//
+// Pixel classes (bit e of the lane's masks, e = line of the warp's slab):
+//   staged  : all four taps inside the staged box and the frame        -> LDS gather
+//   fill    : the coordinate is outside the frame ([1, n] exact, [1, n) fast) -> fill value
+//   skip    : the output pixel itself is outside the frame (partial strip / last tile)
+//   neither : generic path (per-pixel checks, direct global taps): x == n exactly, or a
+//             footprint that leaves the box.  Results never depend on the class.
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
@@ -115,11 +128,9 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                      const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
                      const double* __restrict__ q2tab, RectSched* __restrict__ sched,
                      const float* __restrict__ src, float* __restrict__ dst, float fill) {
-    constexpr int KB = EXACT ? kBatchExact : kBatchFast;
     constexpr int TL = kTLf;                      // lines per tile
-    constexpr int WX = kWXf, WY = kWarps / WX;    // consumer warps across / down the tile
-    constexpr int LPW = TL / WY;                  // lines per warp per tile
-    static_assert(LPW % KB == 0, "batch must divide the lines of a warp");
+    constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
+    static_assert(LPW % 2 == 0 && LPW <= 16, "pairs of lines; masks are 16 bits");
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemRing ring;
     const int lane_id = threadIdx.x & 31;
@@ -132,10 +143,18 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     }
 
     // ---- consumer warps
-    const int wx = warp % WX, wy = warp / WX;
     const unsigned pitch = (unsigned)g.pitch;
     const uint32_t box_pitch_b = (uint32_t)cfg.box1 * 4u;
     const uint32_t stage0 = smem_u32(stage_mem);
+
+    // the map of the current unit
+    uint32_t rel[LPW];                                 // tap (0,0) byte offset inside a stage
+    [[maybe_unused]] double wd1[LPW], wd2[LPW];        // exact weights
+    [[maybe_unused]] float2 wf1[LPW / 2], wf2[LPW / 2];   // fast weights, pairs of lines
+    uint32_t m_staged = 0, m_fill = 0, m_skip = 0;
+    bool all_staged = false;                           // warp-uniform: every pixel of every lane staged
+    int a = 0, b0 = 0;
+    long long off0 = 0;
 
     int s = 0;
     uint32_t phase = 0;
@@ -143,106 +162,135 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         mbar_wait(&ring.full[s], phase);
         const int4 pos = ring.pos[s];
         if (pos.z < 0) break;
-        const TileHdr* h = &ring.hdr[s];
-        const int a_w = pos.x * (kT * WX) + wx * kT;           // first pixel of this warp's lanes
-        const int a = a_w + lane_id;
-        const int b0 = pos.y * TL + wy * LPW;
-        const float* sframe = src + (long long)pos.z * g.frame_stride;
-        float* optr = dst + (long long)pos.z * g.frame_stride + (long long)b0 * g.pitch + a;
-        [[maybe_unused]] RowTermD rtd;
-        [[maybe_unused]] RowTermF rtf;
-        const int a_c = min(a, g.sz1 - 1);             // out-of-frame lanes shadow the last pixel
-        if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-        [[maybe_unused]] double Mk1 = 0, Mk2 = 0;
-        [[maybe_unused]] float mk1 = 0, mk2 = 0;
-        if (EXACT) { Mk1 = h->Mk1; Mk2 = h->Mk2; } else { mk1 = h->mk1; mk2 = h->mk2; }
-        uint32_t R1 = h->R1;
-        const uint32_t R2 = h->R2;
-        if (!(a_w + kT <= g.sz1 && b0 + LPW <= g.sz2)) R1 = 0;   // partial lines: everything generic
-        // raw magic-biased bits index the box directly: fold the bias into the base
-        const uint32_t magic = EXACT ? 0u : (uint32_t)kMagicBits;
-        const uint32_t base = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes + h->base_off - magic * (box_pitch_b + 4u);
-        [[maybe_unused]] float2 ip;
-        ip.x = (float)(g.axs1 + b0) - pf.c2;
-        ip.y = ip.x + 1.0f;
-        [[maybe_unused]] const double* q2p = &ring.q2[s][wy * LPW];
-#pragma unroll 1
-        for (int batch = 0; batch < LPW / KB; ++batch) {
-            uint32_t t1[KB], t2[KB];
-            uint32_t m1 = 0, m2 = 0;
-            [[maybe_unused]] uint32_t hi_bad = 0;
-            [[maybe_unused]] double d1d[KB], d2d[KB];
-            [[maybe_unused]] float2 d1p[KB / 2 + 1], d2p[KB / 2 + 1];
-            if (EXACT) {
+        if (pos.w) {                                   // ---- first frame of a unit: build the map
+            const TileHdr* h = &ring.hdr[s];
+            const int a_w = pos.x * kT;
+            a = a_w + lane_id;
+            b0 = pos.y * TL + warp * LPW;
+            off0 = (long long)b0 * g.pitch + a;
+            const int a_c = min(a, g.sz1 - 1);         // out-of-frame lanes shadow the last pixel
+            const uint32_t R1 = h->R1, R2 = h->R2;
+            const uint32_t rel0 = h->base_off;
+            m_staged = m_fill = m_skip = 0;
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
+            for (int e = 0; e < LPW; ++e)
+                if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
+            if (EXACT) {
+                const RowTermD rtd = rect_row_term(pe, g.axs0 + a_c);
+                const double Mk1 = h->Mk1, Mk2 = h->Mk2;
+                const double* q2p = &ring.q2[s][warp * LPW];
+#pragma unroll
+                for (int e = 0; e < LPW; ++e) {
                     double row, col;
                     rect_coord_nobranch(pe, rtd, q2p[e], row, col);
-                    uint32_t h1, h2;
-                    floor_index<kFloorMode1>(row, Mk1, t1[e], h1, d1d[e]);
-                    floor_index<kFloorMode2>(col, Mk2, t2[e], h2, d2d[e]);
-                    hi_bad |= (h1 ^ 0x43300000u) | (h2 ^ 0x43300000u);
-                    m1 = max(m1, t1[e]);
-                    m2 = max(m2, t2[e]);
+                    uint32_t t1, t2, h1, h2;
+                    floor_index<kFloorMode1>(row, Mk1, t1, h1, wd1[e]);
+                    floor_index<kFloorMode2>(col, Mk2, t2, h2, wd2[e]);
+                    const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
+                    const bool inframe = lin_ok(row, g.sz1) & lin_ok(col, g.sz2);
+                    rel[e] = rel0 + t2 * box_pitch_b + t1 * 4u;
+                    if (st) m_staged |= 1u << e;
+                    if (!inframe) m_fill |= 1u << e;
                 }
-                q2p += KB;
             } else {
+                const RowTermF rtf = rect_row_term(pf, g.axs0 + a_c);
+                const float mk1 = h->mk1, mk2 = h->mk2;
+                float2 ip;
+                ip.x = (float)(g.axs1 + b0) - pf.c2;
+                ip.y = ip.x + 1.0f;
 #pragma unroll
-                for (int hh = 0; hh < KB / 2; ++hh) {
+                for (int hh = 0; hh < LPW / 2; ++hh) {
                     float2 row, col;
                     rect_coord2(pf, rtf, ip, row, col);
                     ip = add2(ip, bc2(2.0f));
-                    floor_bits_fast2(row, mk1, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
-                    floor_bits_fast2(col, mk2, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
-                }
+                    uint32_t t1[2], t2[2];
+                    floor_bits_fast2(row, mk1, t1[0], t1[1], wf1[hh]);
+                    floor_bits_fast2(col, mk2, t2[0], t2[1], wf2[hh]);
+                    const float rr[2] = {row.x, row.y}, cc_[2] = {col.x, col.y};
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
-                    m1 = max(m1, t1[e] - (uint32_t)kMagicBits);
-                    m2 = max(m2, t2[e] - (uint32_t)kMagicBits);
+                    for (int j = 0; j < 2; ++j) {
+                        const int e = 2 * hh + j;
+                        const uint32_t l1 = t1[j] - (uint32_t)kMagicBits, l2 = t2[j] - (uint32_t)kMagicBits;
+                        const bool st = (l1 < R1) & (l2 < R2);
+                        const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
+                        rel[e] = rel0 + l2 * box_pitch_b + l1 * 4u;
+                        if (st) m_staged |= 1u << e;
+                        if (!inframe) m_fill |= 1u << e;
+                    }
                 }
             }
-            bool ok = (m1 < R1) & (m2 < R2);
-            if (EXACT) ok &= hi_bad == 0u;
-            if (__all_sync(0xffffffffu, ok)) {
-                float a00[KB], a10[KB], a01[KB], a11[KB];
+            // a tile the plan marked unusable (P3 not sane, empty box): everything generic
+            if (R1 == 0u || R2 == 0u) { m_staged = 0; m_fill = 0; }
+            constexpr uint32_t kAll = (1u << LPW) - 1u;
+            all_staged = __all_sync(0xffffffffu, (m_staged == kAll) & (m_skip == 0u));
+        }
+
+        // ---- every frame of the unit: gather, blend, store
+        const float* sframe = src + (long long)pos.z * g.frame_stride;
+        float* o = dst + (long long)pos.z * g.frame_stride + off0;
+        const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+        if (all_staged) {
+            float a00[LPW], a10[LPW], a01[LPW], a11[LPW];
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
-                    const uint32_t q = base + t2[e] * box_pitch_b + t1[e] * 4u;
-                    const uint32_t q1 = q + box_pitch_b;
+            for (int e = 0; e < LPW; ++e) {
+                const uint32_t q = sbase + rel[e];
+                const uint32_t q1 = q + box_pitch_b;
 #ifdef CAMCAL_CHECK_BOUNDS      // debug builds (profiles/mkvariant.sh chk "-DCAMCAL_CHECK_BOUNDS"): taps inside the stage
-                    {
-                        const uint32_t lo = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
-                        if (q < lo || q1 + 8u > lo + (uint32_t)cfg.box_bytes || (q & 3u)) __trap();
-                    }
+                if (q < sbase || q1 + 8u > sbase + (uint32_t)cfg.box_bytes || (q & 3u)) __trap();
 #endif
-                    a00[e] = lds_f32(q); a10[e] = lds_f32_off<4>(q);
-                    a01[e] = lds_f32(q1); a11[e] = lds_f32_off<4>(q1);
-                }
-                float* o = optr;
-                if (EXACT) {
+                a00[e] = lds_f32(q); a10[e] = lds_f32_off<4>(q);
+                a01[e] = lds_f32(q1); a11[e] = lds_f32_off<4>(q1);
+            }
+            if (EXACT) {
 #pragma unroll
-                    for (int e = 0; e < KB; ++e) {
-                        const float v = (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e],
-                                                      (double)a11[e], d1d[e], d2d[e]);
-                        __stcs(o, v);
-                        o += pitch;
-                    }
-                } else {
-#pragma unroll
-                    for (int hh = 0; hh < KB / 2; ++hh) {
-                        const float2 v = bilerp_fast2(make_float2(a00[2 * hh], a00[2 * hh + 1]),
-                                                      make_float2(a10[2 * hh], a10[2 * hh + 1]),
-                                                      make_float2(a01[2 * hh], a01[2 * hh + 1]),
-                                                      make_float2(a11[2 * hh], a11[2 * hh + 1]),
-                                                      d1p[hh], d2p[hh]);
-                        __stcs(o, v.x); __stcs(o + pitch, v.y);
-                        o += 2 * pitch;
-                    }
+                for (int e = 0; e < LPW; ++e) {
+                    __stcs(o, (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
+                                            wd1[e], wd2[e]));
+                    o += pitch;
                 }
             } else {
-                generic_lines_f32<EXACT>(&pe, &pf, &g, sframe, optr, a, b0 + batch * KB, KB, fill);
+#pragma unroll
+                for (int hh = 0; hh < LPW / 2; ++hh) {
+                    const float2 v = bilerp_fast2(make_float2(a00[2 * hh], a00[2 * hh + 1]),
+                                                  make_float2(a10[2 * hh], a10[2 * hh + 1]),
+                                                  make_float2(a01[2 * hh], a01[2 * hh + 1]),
+                                                  make_float2(a11[2 * hh], a11[2 * hh + 1]), wf1[hh], wf2[hh]);
+                    __stcs(o, v.x); __stcs(o + pitch, v.y);
+                    o += 2 * pitch;
+                }
             }
-            optr += (long long)KB * pitch;
+        } else {
+            // border tiles: per-pixel class
+#pragma unroll 1
+            for (int e = 0; e < LPW; ++e, o += pitch) {
+                if ((m_skip >> e) & 1u) continue;
+                float v;
+                if ((m_staged >> e) & 1u) {
+                    // (rel[], weights indexed dynamically would spill: select through a switch-free copy)
+                    uint32_t r = 0;
+                    [[maybe_unused]] double d1 = 0, d2 = 0;
+                    [[maybe_unused]] float f1 = 0, f2 = 0;
+#pragma unroll
+                    for (int j = 0; j < LPW; ++j)
+                        if (j == e) {
+                            r = rel[j];
+                            if (EXACT) { d1 = wd1[j]; d2 = wd2[j]; }
+                            else { f1 = (j & 1) ? wf1[j / 2].y : wf1[j / 2].x; f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x; }
+                        }
+                    const uint32_t q = sbase + r, q1 = q + box_pitch_b;
+                    const float t00 = lds_f32(q), t10 = lds_f32_off<4>(q), t01 = lds_f32(q1), t11 = lds_f32_off<4>(q1);
+                    v = EXACT ? (float)bilerp((double)t00, (double)t10, (double)t01, (double)t11, d1, d2)
+                              : bilerp_fast(t00, t10, t01, t11, f1, f2);
+                } else if ((m_fill >> e) & 1u) {
+                    v = fill;
+                } else {
+                    RowTermD rtd;
+                    RowTermF rtf;
+                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+                    v = sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b0 + e, fill);
+                }
+                __stcs(o, v);
+            }
         }
         __syncwarp();
         if (lane_id == 0) mbar_arrive(&ring.empty[s]);

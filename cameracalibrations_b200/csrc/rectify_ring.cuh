@@ -1,8 +1,8 @@
 // rectify_ring.cuh -- scheduling and producer side shared by the staged rectification kernels.
 //
-// Persistent CTAs fed from a global ticket counter.  A work unit is one tile (strip x, tile y,
-// frame z), numbered x fastest, and units are handed out in that order to whichever CTA has a
-// free stage: at any instant the device works on a window of consecutive units, so tiles that
+// Persistent CTAs fed from a global ticket counter.  A work unit is one tile (strip x, tile y)
+// of a GROUP of consecutive frames, numbered x fastest, and units are handed out in that order to
+// whichever CTA is free: at any instant the device works on a window of consecutive units, so tiles that
 // share source lines (the halos of neighbouring strips) are fetched within microseconds of each
 // other and the second fetch hits L2.  Static schedules (long private walks, round-robin) let
 // the CTAs drift apart and were measured to read 1.5x the frame from DRAM
@@ -33,7 +33,10 @@ __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
     return __shfl_sync(0xffffffffu, u, 0);
 }
 
-// PXB: tensor-map elements per pixel along the first axis (1: f32c1, 3: u8c3 bytes)
+// PXB: tensor-map elements per pixel along the first axis (1: f32c1, 3: u8c3 bytes).
+// A unit is (strip x, tile y, frame group): the producer publishes one slot per FRAME of the
+// group -- pos = (x, y, frame, 1 on the first frame of a unit) -- so the consumers rebuild the
+// tile's map only when pos.w is set and otherwise just gather.
 template <bool EXACT, int TL, int PXB>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const RectGeom& g, const TileCfg& cfg,
                                               const TileHdr* __restrict__ plan,
@@ -45,43 +48,44 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const Rec
     uint32_t u_next = take_ticket(sched, lane_id);
     for (;;) {
         const uint32_t u = u_next;
-        const bool live = u < cfg.units;
-        int x = 0, y = 0, z = 0;
+        if (u >= cfg.units) break;
+        const int x = (int)(u % (uint32_t)cfg.strips);
+        const uint32_t r = u / (uint32_t)cfg.strips;
+        const int y = (int)(r % (uint32_t)cfg.ntiles2);
+        const int f0 = (int)(r / (uint32_t)cfg.ntiles2) * cfg.fg;
+        const int f1 = min(f0 + cfg.fg, g.nframes);
+        const uint32_t* hp = reinterpret_cast<const uint32_t*>(plan + x * cfg.ntiles2 + y);
         uint32_t hword = 0;
+        if (lane_id < 12) hword = __ldg(hp + lane_id);            // the 48-byte header, one word per lane
         [[maybe_unused]] double q2a = 0, q2b = 0;
-        if (live) {
-            x = (int)(u % (uint32_t)cfg.strips);
-            const uint32_t r = u / (uint32_t)cfg.strips;
-            y = (int)(r % (uint32_t)cfg.ntiles2);
-            z = (int)(r / (uint32_t)cfg.ntiles2);
-            const uint32_t* hp = reinterpret_cast<const uint32_t*>(plan + x * cfg.ntiles2 + y);
-            if (lane_id < 12) hword = __ldg(hp + lane_id);        // the 48-byte header, one word per lane
-            if (EXACT) {
-                const int b = y * TL + lane_id;
-                q2a = __ldg(q2tab + min(b, g.sz2 - 1));
-                if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
-            }
-            u_next = take_ticket(sched, lane_id);
-        }
-        mbar_wait<kProducerSleep>(&ring->empty[s], phase);
-        if (!live) {
-            if (lane_id == 0) { ring->pos[s] = make_int4(0, 0, -1, 0); mbar_arrive(&ring->full[s]); }
-            break;
-        }
-        if (lane_id < 12) reinterpret_cast<uint32_t*>(&ring->hdr[s])[lane_id] = hword;
-        if (lane_id == 12) ring->pos[s] = make_int4(x, y, z, 0);
         if (EXACT) {
-            if (lane_id < TL) ring->q2[s][lane_id] = q2a;
-            if (TL > 32) ring->q2[s][lane_id + 32] = q2b;
+            const int b = y * TL + lane_id;
+            q2a = __ldg(q2tab + min(b, g.sz2 - 1));
+            if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
         }
+        u_next = take_ticket(sched, lane_id);
         const int x0 = __shfl_sync(0xffffffffu, (int)hword, 8), y0 = __shfl_sync(0xffffffffu, (int)hword, 9);
-        __syncwarp();
-        if (lane_id == 0) {
-            mbar_arrive_expect_tx(&ring->full[s], (uint32_t)cfg.box_bytes);
-            tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, tmap, &ring->full[s], x0 * PXB, y0, z);
+        for (int f = f0; f < f1; ++f) {
+            mbar_wait<kProducerSleep>(&ring->empty[s], phase);
+            if (f == f0) {                                        // the map inputs travel with the first frame
+                if (lane_id < 12) reinterpret_cast<uint32_t*>(&ring->hdr[s])[lane_id] = hword;
+                if (EXACT) {
+                    if (lane_id < TL) ring->q2[s][lane_id] = q2a;
+                    if (TL > 32) ring->q2[s][lane_id + 32] = q2b;
+                }
+            }
+            if (lane_id == 12) ring->pos[s] = make_int4(x, y, f, f == f0 ? 1 : 0);
+            __syncwarp();
+            if (lane_id == 0) {
+                mbar_arrive_expect_tx(&ring->full[s], (uint32_t)cfg.box_bytes);
+                tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, tmap, &ring->full[s], x0 * PXB, y0, f);
+            }
+            if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }
-        if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
+    // stop marker
+    mbar_wait<kProducerSleep>(&ring->empty[s], phase);
+    if (lane_id == 0) { ring->pos[s] = make_int4(0, 0, -1, 0); mbar_arrive(&ring->full[s]); }
     // every producer has taken its last ticket before it counts itself out
     if (lane_id == 0 && atomicAdd(&sched->done, 1u) == gridDim.x - 1) {
         sched->next = 0;

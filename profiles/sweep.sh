@@ -1,5 +1,6 @@
 #!/bin/bash
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k rectify 2>&1 | tail -5
-for so in "" profiles/variants/lib_*.so; do
-  CAMCAL_B200_LIB=${so:+$PWD/$so} python profiles/ktime.py c3 2>&1 | grep -v Warning
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q -m gpu -k "rectify or config2 or config3" 2>&1 | tail -5
+CAMCAL_DEBUG=1 python profiles/ktime.py c2 f32 auto 1 2>&1 | grep camcal | head -1
+for fg in 1 4 8 16 32 64; do
+  CAMCAL_FG=$fg python profiles/ktime.py c2 2>&1 | grep -v Warning | sed "s/^default/fg=$fg/"
 done
