@@ -43,26 +43,17 @@ constexpr int kWarps = 4;              // consumer warps per CTA
 #endif
 constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTLf / kWarps of them)
 constexpr int kTLmax = 64;
-#ifndef CAMCAL_FG_MAX
-#define CAMCAL_FG_MAX 16
-#endif
-constexpr int kFGmax = CAMCAL_FG_MAX;  // most frames one unit rectifies with one map
+// most frames one unit rectifies with one map (measured, profiles/r1_rectify.md: the costlier the
+// map, the larger the group; the cheaper, the finer the units for the tail of the ticket queue)
+constexpr int kFGf32Exact = 12, kFGf32Fast = 4, kFGu8Exact = 16, kFGu8Fast = 8;
 #ifndef CAMCAL_TL_U8
-#define CAMCAL_TL_U8 64
+#define CAMCAL_TL_U8 32
 #endif
 constexpr int kTLu = CAMCAL_TL_U8;     // u8c3: lines per tile
 #ifndef CAMCAL_WX_F32
 #define CAMCAL_WX_F32 1
 #endif
 constexpr int kWXf = CAMCAL_WX_F32;    // f32c1: consumer warps side by side along the first axis (tile width 32*kWXf)
-#ifndef CAMCAL_BATCH_EXACT
-#define CAMCAL_BATCH_EXACT 4
-#endif
-constexpr int kBatchExact = CAMCAL_BATCH_EXACT;   // FP64 values cost two registers each: smaller batches, more CTAs
-#ifndef CAMCAL_BATCH_FAST
-#define CAMCAL_BATCH_FAST 4
-#endif
-constexpr int kBatchFast = CAMCAL_BATCH_FAST;
 // floor of the exact path, per axis: 0 = FRND.F64.FLOOR (XU pipe), 1 = DADD.RM (FP64 pipe)
 #ifndef CAMCAL_FLOOR1
 #define CAMCAL_FLOOR1 0
@@ -80,7 +71,7 @@ constexpr int kProducerSleep = CAMCAL_PRODUCER_SLEEP;   // ns between the produc
 #define CAMCAL_MINB 1
 #endif
 #ifndef CAMCAL_MINB_EXACT
-#define CAMCAL_MINB_EXACT 5
+#define CAMCAL_MINB_EXACT 4
 #endif
 // __launch_bounds__ min CTAs/SM of the staged f32c1 kernels (fast / exact coordinates)
 constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
@@ -425,7 +416,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     RectPlan* plan = plan_get(ctx, ch, ratio, g, tw, tl, pxb, st);
     if (!plan || !plan->box_bytes) return false;
     // measured (profiles/r1_rectify.md): occupancy beats ring depth; small boxes afford more stages
-    int stages = std::min(kMaxStages, std::max(2, 24576 / plan->box_bytes));
+    int stages = std::min(kMaxStages, std::max(2, 32768 / plan->box_bytes));
     if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
     while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 
@@ -544,7 +535,7 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     int rc = CC_OK;
     if (tma) {
-        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT * kWXf, kTLf, kFGmax))) return rc;
+        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT * kWXf, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, &gsz)
@@ -593,7 +584,7 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     int rc = CC_OK;
     if (tma) {
-        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLu, 1))) return rc;
+        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLu, exact ? kFGu8Exact : kFGu8Fast))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, &gsz)

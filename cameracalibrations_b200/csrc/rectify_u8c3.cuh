@@ -209,6 +209,23 @@ rectify_u8c3_direct_kernel(const __grid_constant__ RectExact pe, const __grid_co
 }
 
 // ---- staged kernel (persistent; scheduling and producer: rectify_ring.cuh) ------------------
+// Same unit structure as rectify_f32c1_kernel: the map of a tile (tap byte offset, weights, pixel
+// class) is built once per group of frames and kept in registers (8 pixels per lane); every
+// frame then only gathers, blends and stores.  Both coordinate variants blend in FP32 from FP32
+// copies of the weights; the exact variant certifies each rounding and, for the rare pixel that
+// fails, recomputes the FP64 weights and blends in FP64 (oracle order).
+template <bool EXACT>
+__device__ __noinline__ uint32_t reblend_exact_u8(const RectExact* pe, const RectGeom* g, int a, int b,
+                                                  const Taps6 t0, const Taps6 t1) {
+    const RowTermD rtd = rect_row_term(*pe, g->axs0 + a);
+    double row, col, d1, d2;
+    int i1, i2;
+    rect_coord(*pe, rtd, rect_q2(*pe, g->axs1 + b), row, col);
+    lin_floor(row, i1, d1);
+    lin_floor(col, i2, d2);
+    return blend_rgb<true>(t0, t1, d1, d2, 0.f, 0.f);
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksU8Exact : kMinBlocksU8)
 rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
@@ -217,10 +234,10 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const double* __restrict__ q2tab, RectSched* __restrict__ sched,
                     const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
                     unsigned frame_bytes) {
-    constexpr int KB = 4;                         // lines in flight per lane (two packed pairs)
+    constexpr int KB = 4;                         // pixels blended together (two packed pairs)
     constexpr int TL = kTLu;                      // lines per tile
-    constexpr int LPW = TL / kWarps;              // lines per warp per tile
-    static_assert(LPW % KB == 0, "batch must divide the lines of a warp");
+    constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
+    static_assert(LPW % KB == 0 && LPW <= 16, "batches of four lines; masks are 16 bits");
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemRing ring;
     const int lane_id = threadIdx.x & 31;
@@ -242,121 +259,162 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const unsigned wsel = wo == 0 ? 0x4210u : (wo == 1 ? 0x5421u : 0x6542u);
     const int wp1 = min(wp0 + 1, 31);
 
+    // the map of the current unit
+    uint32_t rel[LPW];                                 // first tap's byte offset inside a stage
+    float2 wf1[LPW / 2], wf2[LPW / 2];                 // weights, pairs of lines (FP32 copies when EXACT)
+    uint32_t m_staged = 0, m_fill = 0, m_skip = 0;
+    bool all_staged = false;
+    int a = 0, b0 = 0;
+    long long off0 = 0;
+
     int s = 0;
     uint32_t phase = 0;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
         const int4 pos = ring.pos[s];
         if (pos.z < 0) break;
-        const TileHdr* h = &ring.hdr[s];
-        const int a_w = pos.x * kT;                            // first pixel of this warp's lanes
-        const int a = a_w + lane_id;
-        const int b0 = pos.y * TL + warp * LPW;
-        const uint8_t* sframe = src + (long long)pos.z * g.frame_stride * 3;
-        // the warp's first output byte of line b0 (4-byte aligned: checked on the host)
-        uint8_t* oline = dst + ((long long)pos.z * g.frame_stride + (long long)b0 * g.pitch + a_w) * 3;
-        [[maybe_unused]] RowTermD rtd;
-        [[maybe_unused]] RowTermF rtf;
-        const int a_c = min(a, g.sz1 - 1);             // out-of-frame lanes shadow the last pixel
-        if (EXACT) rtd = rect_row_term(pe, g.axs0 + a_c); else rtf = rect_row_term(pf, g.axs0 + a_c);
-        [[maybe_unused]] double Mk1 = 0, Mk2 = 0;
-        [[maybe_unused]] float mk1 = 0, mk2 = 0;
-        if (EXACT) { Mk1 = h->Mk1; Mk2 = h->Mk2; } else { mk1 = h->mk1; mk2 = h->mk2; }
-        uint32_t R1 = h->R1;
-        const uint32_t R2 = h->R2;
-        if (!(a_w + kT <= g.sz1 && b0 + LPW <= g.sz2)) R1 = 0;   // partial lines: everything generic
-        // raw magic-biased bits index the box directly: fold the bias into the base
-        const uint32_t magic = EXACT ? 0u : (uint32_t)kMagicBits;
-        const uint32_t base = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes + h->base_off - magic * (box_pitch_b + 3u);
-        [[maybe_unused]] float2 ip;
-        ip.x = (float)(g.axs1 + b0) - pf.c2;
-        ip.y = ip.x + 1.0f;
-        [[maybe_unused]] const double* q2p = &ring.q2[s][warp * LPW];
-#pragma unroll 1
-        for (int batch = 0; batch < LPW / KB; ++batch) {
-            uint32_t t1[KB], t2[KB];
-            uint32_t m1 = 0, m2 = 0;
-            [[maybe_unused]] uint32_t hi_bad = 0;
-            [[maybe_unused]] double d1d[KB], d2d[KB];
-            float2 d1p[KB / 2], d2p[KB / 2];
+        if (pos.w) {                                   // ---- first frame of a unit: build the map
+            const TileHdr* h = &ring.hdr[s];
+            const int a_w = pos.x * kT;
+            a = a_w + lane_id;
+            b0 = pos.y * TL + warp * LPW;
+            off0 = ((long long)b0 * g.pitch + a_w) * 3;        // the warp's first output byte of line b0
+            const int a_c = min(a, g.sz1 - 1);         // out-of-frame lanes shadow the last pixel
+            const uint32_t R1 = h->R1, R2 = h->R2;
+            const uint32_t rel0 = h->base_off;
+            m_staged = m_fill = m_skip = 0;
+#pragma unroll
+            for (int e = 0; e < LPW; ++e)
+                if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
             if (EXACT) {
+                const RowTermD rtd = rect_row_term(pe, g.axs0 + a_c);
+                const double Mk1 = h->Mk1, Mk2 = h->Mk2;
+                const double* q2p = &ring.q2[s][warp * LPW];
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
-                    double row, col;
+                for (int e = 0; e < LPW; ++e) {
+                    double row, col, d1, d2;
                     rect_coord_nobranch(pe, rtd, q2p[e], row, col);
-                    uint32_t h1, h2;
-                    floor_index<kFloorMode1>(row, Mk1, t1[e], h1, d1d[e]);
-                    floor_index<kFloorMode2>(col, Mk2, t2[e], h2, d2d[e]);
-                    hi_bad |= (h1 ^ 0x43300000u) | (h2 ^ 0x43300000u);
-                    m1 = max(m1, t1[e]);
-                    m2 = max(m2, t2[e]);
-                }
-                q2p += KB;
-#pragma unroll
-                for (int hh = 0; hh < KB / 2; ++hh) {
-                    d1p[hh] = make_float2((float)d1d[2 * hh], (float)d1d[2 * hh + 1]);
-                    d2p[hh] = make_float2((float)d2d[2 * hh], (float)d2d[2 * hh + 1]);
+                    uint32_t t1, t2, h1, h2;
+                    floor_index<kFloorMode1>(row, Mk1, t1, h1, d1);
+                    floor_index<kFloorMode2>(col, Mk2, t2, h2, d2);
+                    const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
+                    const bool inframe = lin_ok(row, g.sz1) & lin_ok(col, g.sz2);
+                    rel[e] = rel0 + t2 * box_pitch_b + t1 * 3u;
+                    if (e & 1) { wf1[e / 2].y = (float)d1; wf2[e / 2].y = (float)d2; }
+                    else       { wf1[e / 2].x = (float)d1; wf2[e / 2].x = (float)d2; }
+                    if (st) m_staged |= 1u << e;
+                    if (!inframe) m_fill |= 1u << e;
                 }
             } else {
+                const RowTermF rtf = rect_row_term(pf, g.axs0 + a_c);
+                const float mk1 = h->mk1, mk2 = h->mk2;
+                float2 ip;
+                ip.x = (float)(g.axs1 + b0) - pf.c2;
+                ip.y = ip.x + 1.0f;
 #pragma unroll
-                for (int hh = 0; hh < KB / 2; ++hh) {
+                for (int hh = 0; hh < LPW / 2; ++hh) {
                     float2 row, col;
                     rect_coord2(pf, rtf, ip, row, col);
                     ip = add2(ip, bc2(2.0f));
-                    floor_bits_fast2(row, mk1, t1[2 * hh], t1[2 * hh + 1], d1p[hh]);
-                    floor_bits_fast2(col, mk2, t2[2 * hh], t2[2 * hh + 1], d2p[hh]);
-                }
+                    uint32_t t1[2], t2[2];
+                    floor_bits_fast2(row, mk1, t1[0], t1[1], wf1[hh]);
+                    floor_bits_fast2(col, mk2, t2[0], t2[1], wf2[hh]);
+                    const float rr[2] = {row.x, row.y}, cc_[2] = {col.x, col.y};
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
-                    m1 = max(m1, t1[e] - (uint32_t)kMagicBits);
-                    m2 = max(m2, t2[e] - (uint32_t)kMagicBits);
+                    for (int j = 0; j < 2; ++j) {
+                        const int e = 2 * hh + j;
+                        const uint32_t l1 = t1[j] - (uint32_t)kMagicBits, l2 = t2[j] - (uint32_t)kMagicBits;
+                        const bool st = (l1 < R1) & (l2 < R2);
+                        const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
+                        rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
+                        if (st) m_staged |= 1u << e;
+                        if (!inframe) m_fill |= 1u << e;
+                    }
                 }
             }
-            bool ok = (m1 < R1) & (m2 < R2);
-            if (EXACT) ok &= hi_bad == 0u;
-            if (__all_sync(0xffffffffu, ok)) {
+            if (R1 == 0u || R2 == 0u) { m_staged = 0; m_fill = 0; }   // tile the plan marked unusable
+            constexpr uint32_t kAll = (1u << LPW) - 1u;
+            all_staged = __all_sync(0xffffffffu, (m_staged == kAll) & (m_skip == 0u));
+        }
+
+        // ---- every frame of the unit: gather, blend, store
+        const uint8_t* sframe = src + (long long)pos.z * g.frame_stride * 3;
+        uint8_t* oline = dst + (long long)pos.z * g.frame_stride * 3 + off0;
+        const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+        if (all_staged) {
+            uint32_t* ow = reinterpret_cast<uint32_t*>(oline) + lane_id;
+#pragma unroll
+            for (int bt = 0; bt < LPW / KB; ++bt) {
                 Taps6 ta[KB], tb[KB];
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
-                    const uint32_t o = base + t2[e] * box_pitch_b + t1[e] * 3u;
+                for (int j = 0; j < KB; ++j) {
+                    const uint32_t o = sbase + rel[bt * KB + j];
 #ifdef CAMCAL_CHECK_BOUNDS      // debug builds: the six tap bytes of both lines inside the stage
-                    {
-                        const uint32_t lo = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
-                        if (o < lo || o + box_pitch_b + 6u > lo + (uint32_t)cfg.box_bytes) __trap();
-                    }
+                    if (o < sbase || o + box_pitch_b + 6u > sbase + (uint32_t)cfg.box_bytes) __trap();
 #endif
                     const unsigned sel = sel6(o);              // box_pitch_b % 4 == 0: same for both lines
-                    ta[e] = lds6(o, sel);
-                    tb[e] = lds6(o + box_pitch_b, sel);
+                    ta[j] = lds6(o, sel);
+                    tb[j] = lds6(o + box_pitch_b, sel);
                 }
                 uint32_t rgb[KB];
                 [[maybe_unused]] bool amb[KB];
 #pragma unroll
                 for (int hh = 0; hh < KB / 2; ++hh)
-                    blend_rgb2<EXACT>(ta[2 * hh], tb[2 * hh], ta[2 * hh + 1], tb[2 * hh + 1], d1p[hh], d2p[hh],
+                    blend_rgb2<EXACT>(ta[2 * hh], tb[2 * hh], ta[2 * hh + 1], tb[2 * hh + 1],
+                                      wf1[bt * (KB / 2) + hh], wf2[bt * (KB / 2) + hh],
                                       rgb[2 * hh], rgb[2 * hh + 1], amb[2 * hh], amb[2 * hh + 1]);
                 if (EXACT) {
                     bool any = false;
 #pragma unroll
-                    for (int e = 0; e < KB; ++e) any |= amb[e];
+                    for (int j = 0; j < KB; ++j) any |= amb[j];
                     if (__any_sync(0xffffffffu, any)) {        // rare: certify by the FP64 blend
 #pragma unroll
-                        for (int e = 0; e < KB; ++e)
-                            if (amb[e]) rgb[e] = blend_rgb<true>(ta[e], tb[e], d1d[e], d2d[e], 0.f, 0.f);
+                        for (int j = 0; j < KB; ++j)
+                            if (amb[j]) rgb[j] = reblend_exact_u8<true>(&pe, &g, a, b0 + bt * KB + j, ta[j], tb[j]);
                     }
                 }
-                uint32_t* ow = reinterpret_cast<uint32_t*>(oline) + lane_id;
 #pragma unroll
-                for (int e = 0; e < KB; ++e) {
-                    const uint32_t v0 = __shfl_sync(0xffffffffu, rgb[e], wp0);
-                    const uint32_t v1 = __shfl_sync(0xffffffffu, rgb[e], wp1);
+                for (int j = 0; j < KB; ++j) {
+                    const uint32_t v0 = __shfl_sync(0xffffffffu, rgb[j], wp0);
+                    const uint32_t v1 = __shfl_sync(0xffffffffu, rgb[j], wp1);
                     if (lane_id < 24) __stcs(ow, __byte_perm(v0, v1, wsel));
                     ow = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ow) + pitch3);
                 }
-            } else {
-                generic_lines_u8<EXACT>(pe, pf, g, sframe, oline + lane_id * 3, frame_bytes, a, b0 + batch * KB, KB, fill);
             }
-            oline += (long long)KB * pitch3;
+        } else {
+            // border tiles: per-pixel class, byte stores
+            uint8_t* o = oline + lane_id * 3;
+#pragma unroll 1
+            for (int e = 0; e < LPW; ++e, o += pitch3) {
+                if ((m_skip >> e) & 1u) continue;
+                uint32_t v;
+                if ((m_staged >> e) & 1u) {
+                    uint32_t r = 0;
+                    float f1 = 0, f2 = 0;
+#pragma unroll
+                    for (int j = 0; j < LPW; ++j)
+                        if (j == e) {
+                            r = rel[j];
+                            f1 = (j & 1) ? wf1[j / 2].y : wf1[j / 2].x;
+                            f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x;
+                        }
+                    const uint32_t q = sbase + r;
+                    const unsigned sel = sel6(q);
+                    const Taps6 t0 = lds6(q, sel), t1 = lds6(q + box_pitch_b, sel);
+                    uint32_t vq;
+                    bool am, amq;
+                    blend_rgb2<EXACT>(t0, t1, t0, t1, make_float2(f1, f1), make_float2(f2, f2), v, vq, am, amq);
+                    if (EXACT && am) v = reblend_exact_u8<true>(&pe, &g, a, b0 + e, t0, t1);
+                } else if ((m_fill >> e) & 1u) {
+                    v = fill;
+                } else {
+                    RowTermD rtd;
+                    RowTermF rtf;
+                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+                    v = sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b0 + e, fill);
+                }
+                store_rgb(o, v);
+            }
         }
         __syncwarp();
         if (lane_id == 0) mbar_arrive(&ring.empty[s]);
