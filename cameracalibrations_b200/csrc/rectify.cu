@@ -585,7 +585,8 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
     int rc = CC_OK;
     if (tma) {
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLu, exact ? kFGu8Exact : kFGu8Fast))) return rc;
-        const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
+        // + 16: the word-granular gather may read the aligned words that hold the last tap bytes
+        const size_t smem = (size_t)cfg.stages * cfg.box_bytes + 16;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, &gsz)
                         : persistent_grid(ctx, rectify_u8c3_kernel<false>, smem, cfg, &gsz))) return rc;

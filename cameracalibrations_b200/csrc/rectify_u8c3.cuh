@@ -46,6 +46,14 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     return v;
 }
+// six bytes out of the three words at word-aligned shared address wa
+__device__ __forceinline__ Taps6 lds6w(uint32_t wa, unsigned sel) {
+    const uint32_t w0 = lds_u32(wa), w1 = lds_u32_off<4>(wa), w2 = lds_u32_off<8>(wa);
+    Taps6 t;
+    t.lo = __byte_perm(w0, w1, sel);
+    t.hi = __byte_perm(w1, w2, sel);
+    return t;
+}
 // six bytes at shared byte address o (any alignment)
 __device__ __forceinline__ Taps6 lds6(uint32_t o, unsigned sel) {
     const uint32_t wa = o & ~3u;
@@ -260,7 +268,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const int wp1 = min(wp0 + 1, 31);
 
     // the map of the current unit
-    uint32_t rel[LPW];                                 // first tap's byte offset inside a stage
+    uint32_t rel[LPW];                                 // first tap's byte offset inside a stage, rounded down to a word
+    uint32_t selv[LPW];                                // PRMT selector that funnels the 6 tap bytes out of 3 words
     float2 wf1[LPW / 2], wf2[LPW / 2];                 // weights, pairs of lines (FP32 copies when EXACT)
     uint32_t m_staged = 0, m_fill = 0, m_skip = 0;
     bool all_staged = false;
@@ -300,6 +309,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
                     const bool inframe = lin_ok(row, g.sz1) & lin_ok(col, g.sz2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 3u;
+                    selv[e] = sel6(rel[e]);            // stages are 128-byte aligned: (address & 3) == (rel & 3)
+                    rel[e] &= ~3u;
                     if (e & 1) { wf1[e / 2].y = (float)d1; wf2[e / 2].y = (float)d2; }
                     else       { wf1[e / 2].x = (float)d1; wf2[e / 2].x = (float)d2; }
                     if (st) m_staged |= 1u << e;
@@ -327,6 +338,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         const bool st = (l1 < R1) & (l2 < R2);
                         const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
+                        selv[e] = sel6(rel[e]);
+                        rel[e] &= ~3u;
                         if (st) m_staged |= 1u << e;
                         if (!inframe) m_fill |= 1u << e;
                     }
@@ -348,13 +361,13 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 Taps6 ta[KB], tb[KB];
 #pragma unroll
                 for (int j = 0; j < KB; ++j) {
-                    const uint32_t o = sbase + rel[bt * KB + j];
-#ifdef CAMCAL_CHECK_BOUNDS      // debug builds: the six tap bytes of both lines inside the stage
-                    if (o < sbase || o + box_pitch_b + 6u > sbase + (uint32_t)cfg.box_bytes) __trap();
+                    const uint32_t o = sbase + rel[bt * KB + j];       // word aligned
+#ifdef CAMCAL_CHECK_BOUNDS      // debug builds: the three words of both lines inside the stage
+                    if (o < sbase || o + box_pitch_b + 12u > sbase + (uint32_t)cfg.box_bytes + 4u || (o & 3u)) __trap();
 #endif
-                    const unsigned sel = sel6(o);              // box_pitch_b % 4 == 0: same for both lines
-                    ta[j] = lds6(o, sel);
-                    tb[j] = lds6(o + box_pitch_b, sel);
+                    const unsigned sel = selv[bt * KB + j];    // box_pitch_b % 4 == 0: same for both lines
+                    ta[j] = lds6w(o, sel);
+                    tb[j] = lds6w(o + box_pitch_b, sel);
                 }
                 uint32_t rgb[KB];
                 [[maybe_unused]] bool amb[KB];
@@ -389,18 +402,18 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 if ((m_skip >> e) & 1u) continue;
                 uint32_t v;
                 if ((m_staged >> e) & 1u) {
-                    uint32_t r = 0;
+                    uint32_t r = 0, sel = 0;
                     float f1 = 0, f2 = 0;
 #pragma unroll
                     for (int j = 0; j < LPW; ++j)
                         if (j == e) {
                             r = rel[j];
+                            sel = selv[j];
                             f1 = (j & 1) ? wf1[j / 2].y : wf1[j / 2].x;
                             f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x;
                         }
                     const uint32_t q = sbase + r;
-                    const unsigned sel = sel6(q);
-                    const Taps6 t0 = lds6(q, sel), t1 = lds6(q + box_pitch_b, sel);
+                    const Taps6 t0 = lds6w(q, sel), t1 = lds6w(q + box_pitch_b, sel);
                     uint32_t vq;
                     bool am, amq;
                     blend_rgb2<EXACT>(t0, t1, t0, t1, make_float2(f1, f1), make_float2(f2, f2), v, vq, am, amq);
