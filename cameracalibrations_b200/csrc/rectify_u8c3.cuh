@@ -98,6 +98,50 @@ __device__ __forceinline__ float2 byte_f2(uint32_t wp, uint32_t wq, int k) {
                 bc2(-8388608.0f));
 }
 
+// ---- byte-load variant of the gather (CAMCAL_U8_BYTELOADS): the LSU isolates each tap byte
+// (LDS.U8, twelve per pixel instead of six word loads + sixteen PRMT).  The byte's bit pattern IS
+// a float already -- the denormal b * 2^-149 -- so one packed FMUL2 by 2^100 per pair of bytes
+// makes it the normal float b * 2^-49 (exact); the blend runs in that scaled domain (all normal
+// numbers, full relative precision) and the final FFMA2 by 2^49 onto the rounding magic undoes
+// the scale.  No ALU-pipe work is left in the unpacking, which bounded the word-load variant.
+// 0: word loads, 1: byte loads, 2 (default): byte loads for the exact variant only -- measured on
+// c3: word loads 0.346 ms fast / 0.410 ms exact, byte loads 0.359 / 0.392 (the byte loads trade the
+// ALU bound for a shared-memory-pipe bound; the exact variant's certification already loads the ALU)
+#ifndef CAMCAL_U8_BYTELOADS
+#define CAMCAL_U8_BYTELOADS 2
+#endif
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+constexpr float kTwo100 = 1.2676506002282294e30f;      // 2^100
+constexpr float kTwo49 = 562949953421312.0f;           // 2^49
+template <int OFF>
+__device__ __forceinline__ float2 tap_f2(uint32_t op, uint32_t oq) {
+    return mul2(make_float2(__uint_as_float(lds_u8_off<OFF>(op)), __uint_as_float(lds_u8_off<OFF>(oq))), bc2(kTwo100));
+}
+// pixels p and q (first-tap byte addresses op/oq on the upper source line, op1/oq1 on the lower)
+template <bool CERT>
+__device__ __forceinline__ void blend_rgb2_bytes(uint32_t op, uint32_t op1, uint32_t oq, uint32_t oq1, float2 d1,
+                                                 float2 d2, uint32_t& rgb_p, uint32_t& rgb_q, bool& amb_p,
+                                                 bool& amb_q) {
+    const float2 m = bc2(12582912.0f), up = bc2(kTwo49);
+    const float2 vr = bilerp_fast2(tap_f2<0>(op, oq), tap_f2<3>(op, oq), tap_f2<0>(op1, oq1), tap_f2<3>(op1, oq1), d1, d2);
+    const float2 vg = bilerp_fast2(tap_f2<1>(op, oq), tap_f2<4>(op, oq), tap_f2<1>(op1, oq1), tap_f2<4>(op1, oq1), d1, d2);
+    const float2 vb = bilerp_fast2(tap_f2<2>(op, oq), tap_f2<5>(op, oq), tap_f2<2>(op1, oq1), tap_f2<5>(op1, oq1), d1, d2);
+    const float2 fr = fma2(vr, up, m), fg = fma2(vg, up, m), fb = fma2(vb, up, m);     // rint(v) in the low byte
+    rgb_p = __byte_perm(__byte_perm(__float_as_uint(fr.x), __float_as_uint(fg.x), 0x0040), __float_as_uint(fb.x), 0x0410);
+    rgb_q = __byte_perm(__byte_perm(__float_as_uint(fr.y), __float_as_uint(fg.y), 0x0040), __float_as_uint(fb.y), 0x0410);
+    if (CERT) {
+        // v - rint(v): the scaling by 2^49 is exact, the FMA rounds once (|e| <= 0.5, far above ulp)
+        const float2 er = fma2(vr, up, sub2(m, fr)), eg = fma2(vg, up, sub2(m, fg)), eb = fma2(vb, up, sub2(m, fb));
+        amb_p = (fabsf(er.x) > 0.5f - 6.5e-5f) | (fabsf(eg.x) > 0.5f - 6.5e-5f) | (fabsf(eb.x) > 0.5f - 6.5e-5f);
+        amb_q = (fabsf(er.y) > 0.5f - 6.5e-5f) | (fabsf(eg.y) > 0.5f - 6.5e-5f) | (fabsf(eb.y) > 0.5f - 6.5e-5f);
+    }
+}
+
 // distance of a blended value from the integer it rounds to, against the certification bound
 constexpr float kCertThr = 0.5f - 6.5e-5f;
 
@@ -243,6 +287,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
                     unsigned frame_bytes) {
     constexpr int KB = 4;                         // pixels blended together (two packed pairs)
+    constexpr bool kByteLoads = CAMCAL_U8_BYTELOADS == 2 ? EXACT : (CAMCAL_U8_BYTELOADS != 0);
     constexpr int TL = kTLu;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
     static_assert(LPW % KB == 0 && LPW <= 16, "batches of four lines; masks are 16 bits");
@@ -310,7 +355,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const bool inframe = lin_ok(row, g.sz1) & lin_ok(col, g.sz2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 3u;
                     selv[e] = sel6(rel[e]);            // stages are 128-byte aligned: (address & 3) == (rel & 3)
-                    rel[e] &= ~3u;
+                    if (!kByteLoads) rel[e] &= ~3u;
                     if (e & 1) { wf1[e / 2].y = (float)d1; wf2[e / 2].y = (float)d2; }
                     else       { wf1[e / 2].x = (float)d1; wf2[e / 2].x = (float)d2; }
                     if (st) m_staged |= 1u << e;
@@ -339,7 +384,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
                         selv[e] = sel6(rel[e]);
-                        rel[e] &= ~3u;
+                        if (!kByteLoads) rel[e] &= ~3u;
                         if (st) m_staged |= 1u << e;
                         if (!inframe) m_fill |= 1u << e;
                     }
@@ -358,6 +403,32 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             uint32_t* ow = reinterpret_cast<uint32_t*>(oline) + lane_id;
 #pragma unroll
             for (int bt = 0; bt < LPW / KB; ++bt) {
+                uint32_t rgb[KB];
+                [[maybe_unused]] bool amb[KB];
+                if (kByteLoads) {
+#pragma unroll
+                for (int hh = 0; hh < KB / 2; ++hh) {
+                    const uint32_t op = sbase + rel[bt * KB + 2 * hh], oq = sbase + rel[bt * KB + 2 * hh + 1];
+                    blend_rgb2_bytes<EXACT>(op, op + box_pitch_b, oq, oq + box_pitch_b, wf1[bt * (KB / 2) + hh],
+                                            wf2[bt * (KB / 2) + hh], rgb[2 * hh], rgb[2 * hh + 1], amb[2 * hh],
+                                            amb[2 * hh + 1]);
+                }
+                if (EXACT) {
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < KB; ++j) any |= amb[j];
+                    if (__any_sync(0xffffffffu, any)) {        // rare: certify by the FP64 blend
+#pragma unroll
+                        for (int j = 0; j < KB; ++j)
+                            if (amb[j]) {
+                                const uint32_t o = sbase + rel[bt * KB + j];
+                                const unsigned sel = sel6(o);
+                                rgb[j] = reblend_exact_u8<true>(&pe, &g, a, b0 + bt * KB + j, lds6(o, sel),
+                                                                lds6(o + box_pitch_b, sel));
+                            }
+                    }
+                }
+                } else {
                 Taps6 ta[KB], tb[KB];
 #pragma unroll
                 for (int j = 0; j < KB; ++j) {
@@ -369,8 +440,6 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     ta[j] = lds6w(o, sel);
                     tb[j] = lds6w(o + box_pitch_b, sel);
                 }
-                uint32_t rgb[KB];
-                [[maybe_unused]] bool amb[KB];
 #pragma unroll
                 for (int hh = 0; hh < KB / 2; ++hh)
                     blend_rgb2<EXACT>(ta[2 * hh], tb[2 * hh], ta[2 * hh + 1], tb[2 * hh + 1],
@@ -385,6 +454,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         for (int j = 0; j < KB; ++j)
                             if (amb[j]) rgb[j] = reblend_exact_u8<true>(&pe, &g, a, b0 + bt * KB + j, ta[j], tb[j]);
                     }
+                }
                 }
 #pragma unroll
                 for (int j = 0; j < KB; ++j) {
@@ -413,7 +483,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                             f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x;
                         }
                     const uint32_t q = sbase + r;
-                    const Taps6 t0 = lds6w(q, sel), t1 = lds6w(q + box_pitch_b, sel);
+                    const Taps6 t0 = kByteLoads ? lds6(q, sel) : lds6w(q, sel);
+                    const Taps6 t1 = kByteLoads ? lds6(q + box_pitch_b, sel) : lds6w(q + box_pitch_b, sel);
                     uint32_t vq;
                     bool am, amq;
                     blend_rgb2<EXACT>(t0, t1, t0, t1, make_float2(f1, f1), make_float2(f2, f2), v, vq, am, amq);
