@@ -91,19 +91,54 @@ __device__ __forceinline__ uint32_t blend_rgb(const Taps6& t0, const Taps6& t1, 
     return __byte_perm(__byte_perm(r, g, 0x0040), b, 0x0410);
 }
 
-// two pixels at once (FADD2/FFMA2): same arithmetic as blend_rgb<false>
+// Two pixels at once (FMUL2/FFMA2).  A byte's bit pattern IS a float already -- the denormal
+// b * 2^-149 -- so one packed FMUL2 by 2^100 per pair of bytes makes it the normal float b * 2^-49
+// (exact); the blend runs in that scaled domain (all normal numbers, full relative precision) and
+// the final FFMA2 by 2^49 onto the rounding magic undoes the scale.
+constexpr float kTwo100 = 1.2676506002282294e30f;      // 2^100
+constexpr float kTwo49 = 562949953421312.0f;           // 2^49
 __device__ __forceinline__ float2 byte_f2(uint32_t wp, uint32_t wq, int k) {
-    return add2(make_float2(__uint_as_float(__byte_perm(wp, 0x4B000000u, 0x7440u + (unsigned)k)),
-                            __uint_as_float(__byte_perm(wq, 0x4B000000u, 0x7440u + (unsigned)k))),
-                bc2(-8388608.0f));
+    return mul2(make_float2(__uint_as_float(__byte_perm(wp, 0u, 0x4440u + (unsigned)k)),
+                            __uint_as_float(__byte_perm(wq, 0u, 0x4440u + (unsigned)k))), bc2(kTwo100));
+}
+
+// distance of a blended value from the integer it rounds to, against the certification bound
+constexpr float kCertThr = 0.5f - 6.5e-5f;
+
+// scaled blended values -> packed 0x00BBGGRR per pixel (+ certification of the roundings)
+template <bool CERT>
+__device__ __forceinline__ void round_pack2(float2 vr, float2 vg, float2 vb, uint32_t& rgb_p, uint32_t& rgb_q,
+                                            bool& amb_p, bool& amb_q) {
+    const float2 m = bc2(12582912.0f), up = bc2(kTwo49);
+    const float2 fr = fma2(vr, up, m), fg = fma2(vg, up, m), fb = fma2(vb, up, m);     // rint(v) in the low byte
+    rgb_p = __byte_perm(__byte_perm(__float_as_uint(fr.x), __float_as_uint(fg.x), 0x0040), __float_as_uint(fb.x), 0x0410);
+    rgb_q = __byte_perm(__byte_perm(__float_as_uint(fr.y), __float_as_uint(fg.y), 0x0040), __float_as_uint(fb.y), 0x0410);
+    if (CERT) {
+        // v - rint(v): the scaling by 2^49 is exact, the FMA rounds once (|e| <= 0.5, far above ulp)
+        const float2 er = fma2(vr, up, sub2(m, fr)), eg = fma2(vg, up, sub2(m, fg)), eb = fma2(vb, up, sub2(m, fb));
+        amb_p = (fabsf(er.x) > kCertThr) | (fabsf(eg.x) > kCertThr) | (fabsf(eb.x) > kCertThr);
+        amb_q = (fabsf(er.y) > kCertThr) | (fabsf(eg.y) > kCertThr) | (fabsf(eb.y) > kCertThr);
+    }
+}
+
+// CERT: also report (per pixel) whether any channel is too close to a rounding boundary
+template <bool CERT>
+__device__ __forceinline__ void blend_rgb2(const Taps6& p0, const Taps6& p1, const Taps6& q0,
+                                           const Taps6& q1, float2 d1, float2 d2, uint32_t& rgb_p,
+                                           uint32_t& rgb_q, bool& amb_p, bool& amb_q) {
+    const float2 vr = bilerp_fast2(byte_f2(p0.lo, q0.lo, 0), byte_f2(p0.lo, q0.lo, 3),
+                                   byte_f2(p1.lo, q1.lo, 0), byte_f2(p1.lo, q1.lo, 3), d1, d2);
+    const float2 vg = bilerp_fast2(byte_f2(p0.lo, q0.lo, 1), byte_f2(p0.hi, q0.hi, 0),
+                                   byte_f2(p1.lo, q1.lo, 1), byte_f2(p1.hi, q1.hi, 0), d1, d2);
+    const float2 vb = bilerp_fast2(byte_f2(p0.lo, q0.lo, 2), byte_f2(p0.hi, q0.hi, 1),
+                                   byte_f2(p1.lo, q1.lo, 2), byte_f2(p1.hi, q1.hi, 1), d1, d2);
+    round_pack2<CERT>(vr, vg, vb, rgb_p, rgb_q, amb_p, amb_q);
 }
 
 // ---- byte-load variant of the gather (CAMCAL_U8_BYTELOADS): the LSU isolates each tap byte
-// (LDS.U8, twelve per pixel instead of six word loads + sixteen PRMT).  The byte's bit pattern IS
-// a float already -- the denormal b * 2^-149 -- so one packed FMUL2 by 2^100 per pair of bytes
-// makes it the normal float b * 2^-49 (exact); the blend runs in that scaled domain (all normal
-// numbers, full relative precision) and the final FFMA2 by 2^49 onto the rounding magic undoes
-// the scale.  No ALU-pipe work is left in the unpacking, which bounded the word-load variant.
+// (LDS.U8, twelve per pixel instead of six word loads + sixteen PRMT); the zero-extended byte goes
+// through the same denormal scaling as byte_f2.  No ALU-pipe work is left in the unpacking, which
+// bounds the word-load variant; the shared-memory pipe carries twice the loads instead.
 // 0: word loads, 1: byte loads, 2 (default): byte loads for the exact variant only -- measured on
 // c3: word loads 0.346 ms fast / 0.410 ms exact, byte loads 0.359 / 0.392 (the byte loads trade the
 // ALU bound for a shared-memory-pipe bound; the exact variant's certification already loads the ALU)
@@ -116,8 +151,6 @@ __device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     return v;
 }
-constexpr float kTwo100 = 1.2676506002282294e30f;      // 2^100
-constexpr float kTwo49 = 562949953421312.0f;           // 2^49
 template <int OFF>
 __device__ __forceinline__ float2 tap_f2(uint32_t op, uint32_t oq) {
     return mul2(make_float2(__uint_as_float(lds_u8_off<OFF>(op)), __uint_as_float(lds_u8_off<OFF>(oq))), bc2(kTwo100));
@@ -127,44 +160,10 @@ template <bool CERT>
 __device__ __forceinline__ void blend_rgb2_bytes(uint32_t op, uint32_t op1, uint32_t oq, uint32_t oq1, float2 d1,
                                                  float2 d2, uint32_t& rgb_p, uint32_t& rgb_q, bool& amb_p,
                                                  bool& amb_q) {
-    const float2 m = bc2(12582912.0f), up = bc2(kTwo49);
     const float2 vr = bilerp_fast2(tap_f2<0>(op, oq), tap_f2<3>(op, oq), tap_f2<0>(op1, oq1), tap_f2<3>(op1, oq1), d1, d2);
     const float2 vg = bilerp_fast2(tap_f2<1>(op, oq), tap_f2<4>(op, oq), tap_f2<1>(op1, oq1), tap_f2<4>(op1, oq1), d1, d2);
     const float2 vb = bilerp_fast2(tap_f2<2>(op, oq), tap_f2<5>(op, oq), tap_f2<2>(op1, oq1), tap_f2<5>(op1, oq1), d1, d2);
-    const float2 fr = fma2(vr, up, m), fg = fma2(vg, up, m), fb = fma2(vb, up, m);     // rint(v) in the low byte
-    rgb_p = __byte_perm(__byte_perm(__float_as_uint(fr.x), __float_as_uint(fg.x), 0x0040), __float_as_uint(fb.x), 0x0410);
-    rgb_q = __byte_perm(__byte_perm(__float_as_uint(fr.y), __float_as_uint(fg.y), 0x0040), __float_as_uint(fb.y), 0x0410);
-    if (CERT) {
-        // v - rint(v): the scaling by 2^49 is exact, the FMA rounds once (|e| <= 0.5, far above ulp)
-        const float2 er = fma2(vr, up, sub2(m, fr)), eg = fma2(vg, up, sub2(m, fg)), eb = fma2(vb, up, sub2(m, fb));
-        amb_p = (fabsf(er.x) > 0.5f - 6.5e-5f) | (fabsf(eg.x) > 0.5f - 6.5e-5f) | (fabsf(eb.x) > 0.5f - 6.5e-5f);
-        amb_q = (fabsf(er.y) > 0.5f - 6.5e-5f) | (fabsf(eg.y) > 0.5f - 6.5e-5f) | (fabsf(eb.y) > 0.5f - 6.5e-5f);
-    }
-}
-
-// distance of a blended value from the integer it rounds to, against the certification bound
-constexpr float kCertThr = 0.5f - 6.5e-5f;
-
-// CERT: also report (per pixel) whether any channel is too close to a rounding boundary
-template <bool CERT>
-__device__ __forceinline__ void blend_rgb2(const Taps6& p0, const Taps6& p1, const Taps6& q0,
-                                           const Taps6& q1, float2 d1, float2 d2, uint32_t& rgb_p,
-                                           uint32_t& rgb_q, bool& amb_p, bool& amb_q) {
-    const float2 m = bc2(12582912.0f);
-    const float2 vr = bilerp_fast2(byte_f2(p0.lo, q0.lo, 0), byte_f2(p0.lo, q0.lo, 3),
-                                   byte_f2(p1.lo, q1.lo, 0), byte_f2(p1.lo, q1.lo, 3), d1, d2);
-    const float2 vg = bilerp_fast2(byte_f2(p0.lo, q0.lo, 1), byte_f2(p0.hi, q0.hi, 0),
-                                   byte_f2(p1.lo, q1.lo, 1), byte_f2(p1.hi, q1.hi, 0), d1, d2);
-    const float2 vb = bilerp_fast2(byte_f2(p0.lo, q0.lo, 2), byte_f2(p0.hi, q0.hi, 1),
-                                   byte_f2(p1.lo, q1.lo, 2), byte_f2(p1.hi, q1.hi, 1), d1, d2);
-    const float2 fr = add2(vr, m), fg = add2(vg, m), fb = add2(vb, m);
-    rgb_p = __byte_perm(__byte_perm(__float_as_uint(fr.x), __float_as_uint(fg.x), 0x0040), __float_as_uint(fb.x), 0x0410);
-    rgb_q = __byte_perm(__byte_perm(__float_as_uint(fr.y), __float_as_uint(fg.y), 0x0040), __float_as_uint(fb.y), 0x0410);
-    if (CERT) {
-        const float2 er = sub2(vr, sub2(fr, m)), eg = sub2(vg, sub2(fg, m)), eb = sub2(vb, sub2(fb, m));
-        amb_p = (fabsf(er.x) > kCertThr) | (fabsf(eg.x) > kCertThr) | (fabsf(eb.x) > kCertThr);
-        amb_q = (fabsf(er.y) > kCertThr) | (fabsf(eg.y) > kCertThr) | (fabsf(eb.y) > kCertThr);
-    }
+    round_pack2<CERT>(vr, vg, vb, rgb_p, rgb_q, amb_p, amb_q);
 }
 
 __device__ __forceinline__ void store_rgb(uint8_t* q, uint32_t rgb) {
