@@ -4,8 +4,9 @@
 //
 // Per pixel the two taps of one source line are 6 contiguous bytes at byte offset 3*i: they are
 // fetched as three aligned 32-bit words and funnelled with PRMT.  Bytes become floats without a
-// conversion instruction (PRMT into 0x4B0000bb = 2^23 + b, minus 2^23 in a packed FADD2), the
-// blend runs on PAIRS of lines in FFMA2/FADD2, and the result is rounded by a magic add.
+// conversion instruction (an isolated byte IS the denormal float b * 2^-149; a packed FMUL2 by
+// 2^100 makes it normal and exact), the blend runs on PAIRS of lines in FFMA2/FADD2 in that scaled
+// domain, and the final FFMA2 by 2^49 onto a rounding magic undoes the scale.
 //
 // Exact variant (FP64 coordinates): indices and weights come from the FP64 chain, bit for bit
 // like the oracle.  The blend of 8-bit taps is then done in FP32 with a CERTIFIED rounding:
@@ -135,37 +136,6 @@ __device__ __forceinline__ void blend_rgb2(const Taps6& p0, const Taps6& p1, con
     round_pack2<CERT>(vr, vg, vb, rgb_p, rgb_q, amb_p, amb_q);
 }
 
-// ---- byte-load variant of the gather (CAMCAL_U8_BYTELOADS): the LSU isolates each tap byte
-// (LDS.U8, twelve per pixel instead of six word loads + sixteen PRMT); the zero-extended byte goes
-// through the same denormal scaling as byte_f2.  No ALU-pipe work is left in the unpacking, which
-// bounds the word-load variant; the shared-memory pipe carries twice the loads instead.
-// 0: word loads, 1: byte loads, 2 (default): byte loads for the exact variant only -- measured on
-// c3: word loads 0.346 ms fast / 0.410 ms exact, byte loads 0.359 / 0.392 (the byte loads trade the
-// ALU bound for a shared-memory-pipe bound; the exact variant's certification already loads the ALU)
-#ifndef CAMCAL_U8_BYTELOADS
-#define CAMCAL_U8_BYTELOADS 2
-#endif
-template <int OFF>
-__device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ float2 tap_f2(uint32_t op, uint32_t oq) {
-    return mul2(make_float2(__uint_as_float(lds_u8_off<OFF>(op)), __uint_as_float(lds_u8_off<OFF>(oq))), bc2(kTwo100));
-}
-// pixels p and q (first-tap byte addresses op/oq on the upper source line, op1/oq1 on the lower)
-template <bool CERT>
-__device__ __forceinline__ void blend_rgb2_bytes(uint32_t op, uint32_t op1, uint32_t oq, uint32_t oq1, float2 d1,
-                                                 float2 d2, uint32_t& rgb_p, uint32_t& rgb_q, bool& amb_p,
-                                                 bool& amb_q) {
-    const float2 vr = bilerp_fast2(tap_f2<0>(op, oq), tap_f2<3>(op, oq), tap_f2<0>(op1, oq1), tap_f2<3>(op1, oq1), d1, d2);
-    const float2 vg = bilerp_fast2(tap_f2<1>(op, oq), tap_f2<4>(op, oq), tap_f2<1>(op1, oq1), tap_f2<4>(op1, oq1), d1, d2);
-    const float2 vb = bilerp_fast2(tap_f2<2>(op, oq), tap_f2<5>(op, oq), tap_f2<2>(op1, oq1), tap_f2<5>(op1, oq1), d1, d2);
-    round_pack2<CERT>(vr, vg, vb, rgb_p, rgb_q, amb_p, amb_q);
-}
-
 __device__ __forceinline__ void store_rgb(uint8_t* q, uint32_t rgb) {
     q[0] = (uint8_t)rgb; q[1] = (uint8_t)(rgb >> 8); q[2] = (uint8_t)(rgb >> 16);
 }
@@ -286,7 +256,6 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
                     unsigned frame_bytes) {
     constexpr int KB = 4;                         // pixels blended together (two packed pairs)
-    constexpr bool kByteLoads = CAMCAL_U8_BYTELOADS == 2 ? EXACT : (CAMCAL_U8_BYTELOADS != 0);
     constexpr int TL = kTLu;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
     static_assert(LPW % KB == 0 && LPW <= 16, "batches of four lines; masks are 16 bits");
@@ -354,7 +323,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const bool inframe = lin_ok(row, g.sz1) & lin_ok(col, g.sz2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 3u;
                     selv[e] = sel6(rel[e]);            // stages are 128-byte aligned: (address & 3) == (rel & 3)
-                    if (!kByteLoads) rel[e] &= ~3u;
+                    rel[e] &= ~3u;
                     if (e & 1) { wf1[e / 2].y = (float)d1; wf2[e / 2].y = (float)d2; }
                     else       { wf1[e / 2].x = (float)d1; wf2[e / 2].x = (float)d2; }
                     if (st) m_staged |= 1u << e;
@@ -383,7 +352,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
                         selv[e] = sel6(rel[e]);
-                        if (!kByteLoads) rel[e] &= ~3u;
+                        rel[e] &= ~3u;
                         if (st) m_staged |= 1u << e;
                         if (!inframe) m_fill |= 1u << e;
                     }
@@ -404,30 +373,6 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             for (int bt = 0; bt < LPW / KB; ++bt) {
                 uint32_t rgb[KB];
                 [[maybe_unused]] bool amb[KB];
-                if (kByteLoads) {
-#pragma unroll
-                for (int hh = 0; hh < KB / 2; ++hh) {
-                    const uint32_t op = sbase + rel[bt * KB + 2 * hh], oq = sbase + rel[bt * KB + 2 * hh + 1];
-                    blend_rgb2_bytes<EXACT>(op, op + box_pitch_b, oq, oq + box_pitch_b, wf1[bt * (KB / 2) + hh],
-                                            wf2[bt * (KB / 2) + hh], rgb[2 * hh], rgb[2 * hh + 1], amb[2 * hh],
-                                            amb[2 * hh + 1]);
-                }
-                if (EXACT) {
-                    bool any = false;
-#pragma unroll
-                    for (int j = 0; j < KB; ++j) any |= amb[j];
-                    if (__any_sync(0xffffffffu, any)) {        // rare: certify by the FP64 blend
-#pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (amb[j]) {
-                                const uint32_t o = sbase + rel[bt * KB + j];
-                                const unsigned sel = sel6(o);
-                                rgb[j] = reblend_exact_u8<true>(&pe, &g, a, b0 + bt * KB + j, lds6(o, sel),
-                                                                lds6(o + box_pitch_b, sel));
-                            }
-                    }
-                }
-                } else {
                 Taps6 ta[KB], tb[KB];
 #pragma unroll
                 for (int j = 0; j < KB; ++j) {
@@ -453,7 +398,6 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         for (int j = 0; j < KB; ++j)
                             if (amb[j]) rgb[j] = reblend_exact_u8<true>(&pe, &g, a, b0 + bt * KB + j, ta[j], tb[j]);
                     }
-                }
                 }
 #pragma unroll
                 for (int j = 0; j < KB; ++j) {
@@ -482,8 +426,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                             f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x;
                         }
                     const uint32_t q = sbase + r;
-                    const Taps6 t0 = kByteLoads ? lds6(q, sel) : lds6w(q, sel);
-                    const Taps6 t1 = kByteLoads ? lds6(q + box_pitch_b, sel) : lds6w(q + box_pitch_b, sel);
+                    const Taps6 t0 = lds6w(q, sel), t1 = lds6w(q + box_pitch_b, sel);
                     uint32_t vq;
                     bool am, amq;
                     blend_rgb2<EXACT>(t0, t1, t0, t1, make_float2(f1, f1), make_float2(f2, f2), v, vq, am, amq);
