@@ -111,7 +111,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0002)
 
     def start(self):
         if self.nv:
