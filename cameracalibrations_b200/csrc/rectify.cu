@@ -1,28 +1,22 @@
-// rectify.cu -- full-frame rectification (backward warp + bilinear gather).
+// rectify.cu -- full-frame rectification (backward warp + bilinear gather): host side.
 //
 // Replaces warp(img, tform, axs) of src/plot_calibration.jl:40 (tform/axs from
 // image_transformations :15-22 and get_axes :1-6) for batches of frames that share one
-// view.  The map is computed in-kernel and never stored: algorithmic traffic is one read
-// and one write of every pixel (8 B/px fp32 gray, 6 B/px u8 RGB).
+// view.  The map is never stored in memory: algorithmic traffic is one read and one write of
+// every pixel (8 B/px fp32 gray, 6 B/px u8 RGB).
 //
-// Work decomposition.  The first RowCol axis is contiguous in memory.  A CTA owns a STRIP
-// of 32 consecutive first-axis pixels (lane = pixel, so every store instruction writes one
-// full 128-byte line and consecutive lanes sample consecutive source texels) and marches
-// down the second axis in 32 x 32 TILES; warp w owns lines 4w..4w+3 of each tile.  A thread
-// therefore keeps I1 fixed for its whole life: the I1-dependent half of the extrinsic is
-// hoisted out of the pixel loop.  Square tiles keep the source footprint of a tile compact
-// for any in-plane rotation (35 x 35 texels for the bench view, profiles/r1_rectify.md).
+// Decomposition.  The first RowCol axis is contiguous in memory.  A tile is 32 consecutive
+// first-axis pixels (lane = pixel, so every store instruction writes one full 128-byte line
+// and consecutive lanes sample consecutive source texels) x 32 second-axis lines, 8 lines per
+// consumer warp.  A work unit is one tile of a GROUP of consecutive frames: the tile's map
+// (tap offsets, weights, pixel classes) is built once per unit and reused for every frame of
+// the group (rectify_f32c1.cuh, rectify_u8c3.cuh).
 //
-// Gather.  Two variants of every kernel:
-//  * TMA-staged: a ninth warp is the producer.  For each tile it evaluates the map at the
-//    four tile corners, takes the bounding box of the source footprint and issues ONE
-//    cp.async.bulk.tensor (3-D tensor map over (first axis, second axis, frame)) into a
-//    ring of shared-memory stages guarded by full/empty mbarriers; out-of-frame parts of
-//    the box are zero-filled by the TMA unit.  The eight consumer warps gather their four
-//    taps with LDS from the staged box.  A pixel whose taps are not inside the box (border
-//    tiles, or a footprint larger than the box) falls back to direct global loads, so the
-//    box estimate affects speed only, never results.
-//  * Direct: the same kernel without the producer; taps come through L1/L2 (__ldg).
+// This file: the tile plan (per-tile source box, floor constants, valid ranges; built on the
+// host once per calibration/geometry, cached in the context, uploaded once), the tensor map of
+// the source frames, the persistent grid and its ticket counter (rectify_ring.cuh), and the
+// choice between the TMA-staged kernels and the direct ones (pointers/pitches TMA cannot
+// address, footprints too large to stage).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -50,10 +44,6 @@ constexpr int kFGf32Exact = 12, kFGf32Fast = 4, kFGu8Exact = 16, kFGu8Fast = 8;
 #define CAMCAL_TL_U8 32
 #endif
 constexpr int kTLu = CAMCAL_TL_U8;     // u8c3: lines per tile
-#ifndef CAMCAL_WX_F32
-#define CAMCAL_WX_F32 1
-#endif
-constexpr int kWXf = CAMCAL_WX_F32;    // f32c1: consumer warps side by side along the first axis (tile width 32*kWXf)
 // floor of the exact path, per axis: 0 = FRND.F64.FLOOR (XU pipe), 1 = DADD.RM (FP64 pipe)
 #ifndef CAMCAL_FLOOR1
 #define CAMCAL_FLOOR1 0
@@ -530,12 +520,12 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     TileCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
     RectPlan* plan = nullptr;
-    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, kT * kWXf, kTLf, st, &tmap, &cfg, &plan);
+    const bool tma = !(flags & CC_GATHER_DIRECT) && plan_tma(ctx, chd, ratio, g, src, 4, kT, kTLf, st, &tmap, &cfg, &plan);
     if ((flags & CC_GATHER_TMA) && !tma)
         return set_error(CC_ERR_INVALID_ARG, "TMA gather not available for this layout / footprint");
     int rc = CC_OK;
     if (tma) {
-        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT * kWXf, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
+        if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, &gsz)

@@ -1,19 +1,17 @@
 // rectify_f32c1.cuh -- fp32 single-channel rectification kernels (included by rectify.cu).
 //
-// The per-pixel instruction budget bounds these kernels (profiles/r1_rectify.md), so the staged
-// path is written to the instruction:
-//  * the producer folds the tile's index origin into the floor constant: the exact path adds
+// Staged kernel: persistent CTAs, ticket scheduler and TMA producer in rectify_ring.cuh; the
+// consumers build a tile's map once per group of frames and reuse it (see the kernel's header).
+// Details that keep the map build short:
+//  * the host plan folds the tile's index origin into the floor constant: the exact path adds
 //    Mk = 2^52 - K to the coordinate with round-down (DADD.RM is the floor) or to
 //    FRND.F64.FLOOR(x), the fast path adds mk = 1.5*2^23 - K with FADD2.RM; the low word of the
-//    sum is magic + tile-local tap index.  "high word == 0x43300000" and
-//    "max over the batch of (bits - magic) < R" are the complete range tests (negative, NaN,
-//    huge and out-of-box coordinates all fail them), and the smem address takes the raw bits
-//    (the magic is folded into the tile's base address);
-//  * 1/P3 is NVIDIA's own correctly rounded sequence (MUFU.RCP64H + 5 DFMA) inlined without
-//    its per-pixel branch: its validity test (exponent of P3 not extreme) is made once per
-//    tile by the producer on the tile corners -- P3 is affine in the output index;
-//  * one vote per batch of lines decides between the staged gather and the generic path,
-//    which lives out of line so that the hot loop keeps its registers.
+//    sum is (magic +) the tile-local tap index, "high word == 0x43300000" and "index < R" are the
+//    complete range tests (negative, NaN, huge and out-of-box coordinates all fail them);
+//  * 1/P3 is NVIDIA's own correctly rounded sequence (MUFU.RCP64H + 5 DFMA) inlined without its
+//    per-pixel branch: its validity test (exponent of P3 not extreme) is made once per tile by
+//    the plan on the tile corners -- P3 is affine in the output index.
+// Direct kernel: no staging, every pixel through sample_direct_f32 (layouts TMA cannot address).
 #pragma once
 
 namespace cc {
@@ -47,30 +45,6 @@ __device__ __forceinline__ float sample_direct_f32(const RectExact& pe, const Re
         const float* q = sframe + ((unsigned)g2 * pitch + (unsigned)g1);
         return bilerp_fast(__ldg(q), __ldg(q + 1), __ldg(q + pitch), __ldg(q + pitch + 1), d1, d2);
     }
-}
-
-// `n` consecutive lines of one lane's pixel column through the generic path (cold)
-#ifndef CAMCAL_GENERIC_INLINE
-#define CAMCAL_GENERIC_INLINE 1
-#endif
-#if CAMCAL_GENERIC_INLINE
-#define CC_GENERIC_ATTR __forceinline__
-#else
-#define CC_GENERIC_ATTR __noinline__
-#endif
-template <bool EXACT>
-__device__ CC_GENERIC_ATTR void generic_lines_f32(const RectExact* pe, const RectFast* pf, const RectGeom* g,
-                                               const float* __restrict__ sframe, float* __restrict__ o,
-                                               int a, int b, int n, float fill) {
-    if (a >= g->sz1) return;
-    RowTermD rtd;
-    RowTermF rtf;
-    if (EXACT) rtd = rect_row_term(*pe, g->axs0 + a); else rtf = rect_row_term(*pf, g->axs0 + a);
-    const unsigned pitch = (unsigned)g->pitch;
-    n = min(n, g->sz2 - b);
-#pragma unroll 1
-    for (int e = 0; e < n; ++e, o += pitch)
-        __stcs(o, sample_direct_f32<EXACT>(*pe, *pf, rtd, rtf, *g, sframe, pitch, b + e, fill));
 }
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {

@@ -55,16 +55,6 @@ __device__ __forceinline__ Taps6 lds6w(uint32_t wa, unsigned sel) {
     t.hi = __byte_perm(w1, w2, sel);
     return t;
 }
-// six bytes at shared byte address o (any alignment)
-__device__ __forceinline__ Taps6 lds6(uint32_t o, unsigned sel) {
-    const uint32_t wa = o & ~3u;
-    const uint32_t w0 = lds_u32(wa), w1 = lds_u32_off<4>(wa), w2 = lds_u32_off<8>(wa);
-    Taps6 t;
-    t.lo = __byte_perm(w0, w1, sel);
-    t.hi = __byte_perm(w1, w2, sel);
-    return t;
-}
-
 // byte k of w as a float without a conversion instruction: 0x4B000000 | b  ==  2^23 + b
 __device__ __forceinline__ float byte_f(uint32_t w, int k) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + (unsigned)k)) - 8388608.0f;
@@ -187,22 +177,6 @@ __device__ __forceinline__ uint32_t sample_direct_u8(const RectExact& pe, const 
         t1.hi = q[4] | (q[5] << 8);
     }
     return blend_rgb<EXACT>(t0, t1, d1d, d2d, d1f, d2f);
-}
-
-// `n` consecutive lines of one lane's pixel column through the generic path (cold)
-template <bool EXACT>
-__device__ __forceinline__ void generic_lines_u8(const RectExact& pe, const RectFast& pf, const RectGeom& g,
-                                                 const uint8_t* __restrict__ sframe, uint8_t* __restrict__ o,
-                                                 unsigned frame_bytes, int a, int b, int n, uint32_t fill) {
-    if (a >= g.sz1) return;
-    RowTermD rtd;
-    RowTermF rtf;
-    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
-    const unsigned pitch3 = (unsigned)g.pitch * 3u;
-    n = min(n, g.sz2 - b);
-#pragma unroll 1
-    for (int e = 0; e < n; ++e, o += pitch3)
-        store_rgb(o, sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b + e, fill));
 }
 
 // ---- direct kernel: no staging -------------------------------------------------------------
