@@ -69,7 +69,7 @@ constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
 #define CAMCAL_MINB_U8 1
 #endif
 #ifndef CAMCAL_MINB_U8_EXACT
-#define CAMCAL_MINB_U8_EXACT 1
+#define CAMCAL_MINB_U8_EXACT 4
 #endif
 constexpr int kMinBlocksU8 = CAMCAL_MINB_U8, kMinBlocksU8Exact = CAMCAL_MINB_U8_EXACT;
 constexpr int kConsumerThreads = 32 * kWarps;
