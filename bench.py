@@ -187,7 +187,9 @@ def main():
     config = {"workload": wl["name"], "frame": f"{sz[0]}x{sz[1]}", "frames_per_step_per_gpu": wl["frames"],
               "pixel": "u8x3" if wl["u8"] else "f32x1", "view": BENCH_VIEW, "intr": wl["intr"],
               "coord": args.coord, "parallelism": f"frame-sharded x{args.gpus} (no data-path collective)",
-              "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)"}
+              "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+              "map_reuse": "the rectification map is built once per tile per group of <= 12 (f64) / 4 (f32) "
+                           "frames of the batch and reused; every frame is read and written once per step"}
 
     # ------------------------------------------------------------------ CPU arm
     if args.impl == "reference":
