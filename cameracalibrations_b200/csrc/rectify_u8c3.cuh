@@ -279,9 +279,11 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             const uint32_t R1 = h->R1, R2 = h->R2;
             const uint32_t rel0 = h->base_off;
             m_staged = m_fill = m_skip = 0;
+            if (a_w + kT > g.sz1 || b0 + LPW > g.sz2) {        // partial tile (warp-uniform test)
 #pragma unroll
-            for (int e = 0; e < LPW; ++e)
-                if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
+                for (int e = 0; e < LPW; ++e)
+                    if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
+            }
             if (EXACT) {
                 const RowTermD rtd = rect_row_term(pe, g.axs0 + a_c);
                 const double Mk1 = h->Mk1, Mk2 = h->Mk2;
@@ -294,14 +296,13 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     floor_index<kFloorMode1>(row, Mk1, t1, h1, d1);
                     floor_index<kFloorMode2>(col, Mk2, t2, h2, d2);
                     const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
-                    const bool inframe = lin_ok(row, g.sz1) & lin_ok(col, g.sz2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 3u;
                     selv[e] = sel6(rel[e]);            // stages are 128-byte aligned: (address & 3) == (rel & 3)
                     rel[e] &= ~3u;
                     if (e & 1) { wf1[e / 2].y = (float)d1; wf2[e / 2].y = (float)d2; }
                     else       { wf1[e / 2].x = (float)d1; wf2[e / 2].x = (float)d2; }
                     if (st) m_staged |= 1u << e;
-                    if (!inframe) m_fill |= 1u << e;
+                    else if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) m_fill |= 1u << e;   // rare: border tiles
                 }
             } else {
                 const RowTermF rtf = rect_row_term(pf, g.axs0 + a_c);
@@ -323,12 +324,12 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         const int e = 2 * hh + j;
                         const uint32_t l1 = t1[j] - (uint32_t)kMagicBits, l2 = t2[j] - (uint32_t)kMagicBits;
                         const bool st = (l1 < R1) & (l2 < R2);
-                        const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
                         selv[e] = sel6(rel[e]);
                         rel[e] &= ~3u;
                         if (st) m_staged |= 1u << e;
-                        if (!inframe) m_fill |= 1u << e;
+                        else if (!((rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2)))
+                            m_fill |= 1u << e;                 // rare: border tiles
                     }
                 }
             }
