@@ -362,6 +362,91 @@ def test_rectify_plan_cache_many_parameter_sets(cc):
             assert np.array_equal(got2.cpu().numpy(), refs[i]), i
 
 
+@pytest.mark.parametrize("pad1,padf", [(4, 64), (3, 7), (0, 16)])
+def test_rectify_strided_layouts_through_the_abi(cc, pad1, padf):
+    """pitch > sz1 and frame_stride > pitch * sz2 (the C ABI's layout parameters; the Python warp()
+    always passes dense arrays): TMA-addressable strides (pad 4 px / 64 px) and odd ones (direct
+    kernels).  The valid region equals the dense oracle result, the padding is never written."""
+    from cameracalibrations_b200 import _lib
+    sz = (128, 96)
+    intr = camera_for(sz)
+    ch, ip, ratio, axs = _rect_case(intr, sz)
+    c = _calib(cc, intr, [SYN_VIEW])
+    nf, pitch = 3, sz[0] + pad1
+    stride = pitch * sz[1] + padf
+    rng = np.random.default_rng(8)
+    axs_c = (C.c_int64 * 2)(*axs)
+    h = _lib.context(0).handle
+    ci, cv = C.byref(c._intr), C.byref(c._views[0])
+    # fp32 gray
+    dense = rng.random((nf, sz[1], sz[0]), dtype=np.float32)
+    ref = oc.rectify_f32c1(ch, 1.0 / ratio, axs, dense, fill=-4.0)
+    buf = np.full(nf * stride, 777.0, np.float32)
+    for f in range(nf):
+        buf[f * stride: f * stride + pitch * sz[1]].reshape(sz[1], pitch)[:, :sz[0]] = dense[f]
+    for coord in (_lib.COORD_F64,):
+        src, dst = _dev(buf), _dev(np.full(nf * stride, 555.0, np.float32))
+        _lib.check(_lib.lib.cc_rectify_f32c1(h, ci, cv, float(ratio), axs_c, C.c_void_p(src.data_ptr()),
+                                             C.c_void_p(dst.data_ptr()), sz[0], sz[1], C.c_size_t(pitch),
+                                             C.c_size_t(stride), nf, C.c_float(-4.0), coord, None))
+        torch.cuda.synchronize()
+        out = dst.cpu().numpy()
+        seen = np.zeros(out.shape, bool)
+        for f in range(nf):
+            v = out[f * stride: f * stride + pitch * sz[1]].reshape(sz[1], pitch)
+            assert np.array_equal(v[:, :sz[0]], ref[f])
+            seen[f * stride: f * stride + pitch * sz[1]].reshape(sz[1], pitch)[:, :sz[0]] = True
+        assert np.all(out[~seen] == 555.0)
+    # u8 RGB
+    d8 = rng.integers(0, 256, (nf, sz[1], sz[0], 3), dtype=np.uint8)
+    ref8 = oc.rectify_u8c3(ch, 1.0 / ratio, axs, d8, fill=(1, 2, 3))
+    b8 = np.full(nf * stride * 3, 77, np.uint8)
+    for f in range(nf):
+        b8[f * stride * 3: (f * stride + pitch * sz[1]) * 3].reshape(sz[1], pitch, 3)[:, :sz[0]] = d8[f]
+    src, dst = _dev(b8), _dev(np.full(nf * stride * 3, 55, np.uint8))
+    fill = (C.c_uint8 * 3)(1, 2, 3)
+    _lib.check(_lib.lib.cc_rectify_u8c3(h, ci, cv, float(ratio), axs_c, C.c_void_p(src.data_ptr()),
+                                        C.c_void_p(dst.data_ptr()), sz[0], sz[1], C.c_size_t(pitch),
+                                        C.c_size_t(stride), nf, fill, _lib.COORD_F64, None))
+    torch.cuda.synchronize()
+    out = dst.cpu().numpy()
+    seen = np.zeros(out.shape, bool)
+    for f in range(nf):
+        v = out[f * stride * 3: (f * stride + pitch * sz[1]) * 3].reshape(sz[1], pitch, 3)
+        assert np.array_equal(v[:, :sz[0]], ref8[f])
+        seen[f * stride * 3: (f * stride + pitch * sz[1]) * 3].reshape(sz[1], pitch, 3)[:, :sz[0]] = True
+    assert np.all(out[~seen] == 55)
+
+
+def test_rectify_view_with_a_horizon(cc):
+    """A steeply tilted board: part of the output plane lies behind the camera, so P3 changes sign
+    inside the frame (tiles the plan marks as unusable for the branch-free reciprocal), coordinates
+    run through +-inf, and most pixels are fill.  Every kernel variant equals the oracle."""
+    sz = (256, 192)
+    intr = camera_for(sz)
+    view = ((1.45, 0.1, 0.0), (-3.0, -2.0, 2.0))
+    c = _calib(cc, intr, [view])
+    ch = oc.chain(intr, *view)
+    rng = np.random.default_rng(2)
+    frames = rng.random((2, sz[1], sz[0]), dtype=np.float32)
+    f8 = rng.integers(0, 256, (2, sz[1], sz[0], 3), dtype=np.uint8)
+    for ratio, axs in ((6.0, (-40, -30)), (1.5, (-200, -400))):
+        ref = oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-9.0)
+        ref8 = oc.rectify_u8c3(ch, 1.0 / ratio, axs, f8, fill=(4, 5, 6))
+        for gather in ("auto", "direct"):
+            got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=-9.0, gather=gather).cpu().numpy()
+            assert np.array_equal(got, ref), (ratio, gather)
+            got8 = cc.warp(c, 0, _dev(f8), ratio, axs, fill=(4, 5, 6), gather=gather).cpu().numpy()
+            assert np.array_equal(got8, ref8), (ratio, gather)
+        # the fast path may differ near the horizon only: where the FP64 map is inside the frame
+        # by a margin it samples, elsewhere it fills
+        gotf = cc.warp(c, 0, _dev(frames), ratio, axs, fill=-9.0, coord="f32").cpu().numpy()
+        omr, omc = oc.rectify_map(ch, 1.0 / ratio, axs, sz)
+        far_out = ~((omr > -50) & (omr < sz[0] + 50) & (omc > -50) & (omc < sz[1] + 50))
+        assert np.all(gotf[0][far_out & np.isfinite(omr)] == -9.0)
+    assert 0.01 < (ref != -9.0).mean() < 0.99
+
+
 @pytest.mark.parametrize("intr,sz", [(C2_INTR, (1080, 1920)), (C3_INTR, (2160, 3840))])
 def test_rectify_f32_coords_within_1e3_px(cc, intr, sz):
     """FP32 fast path: warp a row-ramp and a column-ramp; bilinear interpolation reproduces a
