@@ -289,6 +289,16 @@ def main():
                 "algorithmic_bytes_per_launch": wl["bytes_per_px"] * npx}
 
     # ---- e2e: host entry point of the C ABI, pinned host buffers, copies in the timed region
+    # Bind this rank to the CPUs next to its GPU first, so that the pinned buffers (first touch) and
+    # the enqueueing thread sit on the GPU's NUMA node; restored before the CPU baseline leg.
+    cpus_before = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        config["e2e_cpu_affinity"] = f"nvml ideal cpus of gpu {local_rank} ({len(os.sched_getaffinity(0))} of {len(cpus_before)})"
+    except Exception as ex:       # no NVML / not permitted: run unbound
+        config["e2e_cpu_affinity"] = f"unbound ({type(ex).__name__})"
     px_bytes = 3 if wl["u8"] else 4
     shape = tuple(src.shape)
     h_src, p1 = pinned_array(cc, shape, np.uint8 if wl["u8"] else np.float32)
@@ -316,6 +326,10 @@ def main():
     _lib.lib.cc_host_free(p1)
     _lib.lib.cc_host_free(p2)
     del h_src, h_dst
+    try:
+        os.sched_setaffinity(0, cpus_before)
+    except Exception:
+        pass
 
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
