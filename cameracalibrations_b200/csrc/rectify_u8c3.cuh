@@ -279,7 +279,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             const uint32_t R1 = h->R1, R2 = h->R2;
             const uint32_t rel0 = h->base_off;
             m_staged = m_fill = m_skip = 0;
-            if (a_w + kT > g.sz1 || b0 + LPW > g.sz2) {        // partial tile (warp-uniform test)
+            if (!EXACT || a_w + kT > g.sz1 || b0 + LPW > g.sz2) {   // partial tile (warp-uniform test; measured: pays only in the exact kernel)
 #pragma unroll
                 for (int e = 0; e < LPW; ++e)
                     if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
@@ -327,9 +327,10 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
                         selv[e] = sel6(rel[e]);
                         rel[e] &= ~3u;
+                        // (unconditional: four FSETPs cost less than a divergent branch here; measured)
+                        const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         if (st) m_staged |= 1u << e;
-                        else if (!((rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2)))
-                            m_fill |= 1u << e;                 // rare: border tiles
+                        if (!inframe) m_fill |= 1u << e;
                     }
                 }
             }
