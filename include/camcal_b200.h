@@ -132,7 +132,12 @@ int cc_world2img_f32_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
  *      with tform = real2image[i] o push(.,0) o inv(LinearMap(ratio*I)) (:17-18) and
  *      axs from get_axes (:1-6): output index (I1, I2) = axs_min + (a, b), same size
  *      as the input.  Bilinear, OnGrid, out-of-range -> fill.  `ratio` is pixels per
- *      world unit (get_ratio, :8-13).  flags = CC_COORD_* | CC_GATHER_*. */
+ *      world unit (get_ratio, :8-13).  flags = CC_COORD_* | CC_GATHER_*.
+ *      All `nframes` frames share the view: the map is computed once per tile and group of
+ *      frames, so batches rectify faster per frame than single-frame calls.  The first call
+ *      with a new (calibration, ratio, axs_min, frame geometry) builds the tile plan on the host
+ *      and uploads it (one stream synchronisation); later calls with the same parameters are
+ *      fully asynchronous. */
 int cc_rectify_f32c1(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, double ratio,
                      const int64_t axs_min[2], const float *src, float *dst, int sz1,
                      int sz2, size_t pitch, size_t frame_stride, int nframes, float fill,
