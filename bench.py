@@ -435,6 +435,35 @@ def extras(cc, torch, dev, c2cal, args):
         lm.lm_update(sh, schur, 1e-3, lm.FREE_ALL, yz, tv)
     ms = _time_ms(torch, lm_step, 20)
     ex["lm_step_10k_views"] = {"views_per_s": nv / (ms * 1e-3), "ms": ms}
+    # the whole fit (starting values on the host + device LM, CRITERIA 30 / 1e-3) on 100 noisy synthetic
+    # views, and OpenCV's calibrateCamera -- the call the reference makes -- on the same corners (CPU)
+    nvf = 100
+    vf = views[:nvf]
+    c100 = cc.Calibration(wl["intr"][:4], [(v[:3], v[3:]) for v in vf[:1]], 1.0, wl["intr"][4], ["extrinsic.png"])
+    imgs = np.empty((nvf, nc, 2))
+    for i in range(nvf):
+        ci = cc.Calibration(wl["intr"][:4], [(vf[i, :3], vf[i, 3:])], 1.0, wl["intr"][4], ["extrinsic.png"])
+        r_, q_ = ci.world2img(to[:, 0].contiguous(), to[:, 1].contiguous(), to[:, 2].contiguous(), 0)
+        imgs[i, :, 0], imgs[i, :, 1] = r_.cpu().numpy(), q_.cpu().numpy()
+    imgs += rng.normal(0, 0.1, imgs.shape)
+    t0 = time.perf_counter()
+    i0, v0 = lm.initial_guess(obj, imgs, (2160, 3840), 1.0)
+    t1 = time.perf_counter()
+    fit = lm.lm_fit(i0, v0, obj, imgs)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    ex["fit_100_views"] = {"init_host_ms": (t1 - t0) * 1e3, "lm_device_ms": (t2 - t1) * 1e3, "rms_px": fit["rms"],
+                           "iterations": fit["iterations"]}
+    try:
+        import cv2
+        flags = cv2.CALIB_ZERO_TANGENT_DIST + cv2.CALIB_FIX_K3 + cv2.CALIB_FIX_K2 + cv2.CALIB_FIX_ASPECT_RATIO
+        crit = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 30, 0.001)
+        t3 = time.perf_counter()
+        rms = cv2.calibrateCamera([obj.astype(np.float32)] * nvf, [c_.astype(np.float32).reshape(-1, 1, 2) for c_ in imgs],
+                                  (2160, 3840), np.eye(3), np.zeros(5), flags=flags, criteria=crit)[0]
+        ex["fit_100_views"].update({"cv2_calibrateCamera_ms": (time.perf_counter() - t3) * 1e3, "cv2_rms_px": float(rms)})
+    except Exception as e:          # cv2 missing: the comparison is optional
+        ex["fit_100_views"]["cv2"] = f"unavailable ({type(e).__name__})"
     return ex
 
 

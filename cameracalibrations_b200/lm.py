@@ -31,24 +31,30 @@ FREE_NO_K = 0b0111          # CALIB_FIX_K1
 
 
 # ------------------------------------------------------------------ starting values (host, tiny)
-def _homography(xy, rc):
-    """DLT with Hartley normalisation: (x, y, 1) -> (row, col, 1)."""
-    def norm(p):
-        m = p.mean(0)
-        s = np.sqrt(2.0) / max(np.sqrt(((p - m) ** 2).sum(1)).mean(), 1e-300)
-        T = np.array([[s, 0, -s * m[0]], [0, s, -s * m[1]], [0, 0, 1.0]])
-        return (p - m) * s, T
-    a, Ta = norm(xy)
-    b, Tb = norm(rc)
-    n = len(xy)
-    A = np.zeros((2 * n, 9))
-    A[0::2, 0:2], A[0::2, 2] = a, 1.0
-    A[0::2, 6:8], A[0::2, 8] = -b[:, :1] * a, -b[:, 0]
-    A[1::2, 3:5], A[1::2, 5] = a, 1.0
-    A[1::2, 6:8], A[1::2, 8] = -b[:, 1:] * a, -b[:, 1]
-    h = np.linalg.svd(A)[2][-1].reshape(3, 3)
+def _homographies(xy, rcs):
+    """DLT with Hartley normalisation, all views at once: (x, y, 1) -> (row, col, 1).
+    xy (n, 2) board corners, rcs (nv, n, 2) detections.  The 9x9 normal matrices are
+    eigen-decomposed in one batched call (starting values only: the LM refines them)."""
+    def norm(p):                                   # p (..., n, 2) -> normalised points, T (..., 3, 3)
+        m = p.mean(-2, keepdims=True)
+        s = np.sqrt(2.0) / np.maximum(np.sqrt(((p - m) ** 2).sum(-1)).mean(-1), 1e-300)
+        T = np.zeros(p.shape[:-2] + (3, 3))
+        T[..., 0, 0] = T[..., 1, 1] = s
+        T[..., 0, 2], T[..., 1, 2] = -s * m[..., 0, 0], -s * m[..., 0, 1]
+        T[..., 2, 2] = 1.0
+        return (p - m) * s[..., None, None], T
+    a, Ta = norm(np.asarray(xy, float))
+    b, Tb = norm(np.asarray(rcs, float))
+    nv, n = b.shape[0], b.shape[1]
+    A = np.zeros((nv, 2 * n, 9))
+    A[:, 0::2, 0:2], A[:, 0::2, 2] = a, 1.0
+    A[:, 0::2, 6:8], A[:, 0::2, 8] = -b[:, :, :1] * a, -b[:, :, 0]
+    A[:, 1::2, 3:5], A[:, 1::2, 5] = a, 1.0
+    A[:, 1::2, 6:8], A[:, 1::2, 8] = -b[:, :, 1:] * a, -b[:, :, 1]
+    _, vecs = np.linalg.eigh(np.einsum("vij,vik->vjk", A, A))
+    h = vecs[:, :, 0].reshape(nv, 3, 3)            # eigenvector of the smallest eigenvalue
     H = np.linalg.inv(Tb) @ h @ Ta
-    return H / H[2, 2]
+    return H / H[:, 2:3, 2:3]
 
 
 def _rodrigues_inv(R):
@@ -74,7 +80,7 @@ def initial_guess(obj, imgs, sz, aspect=1.0):
     Returns (intr (frow, fcol, crow, ccol, k), views (nv, 6))."""
     obj, imgs = np.asarray(obj, float), np.asarray(imgs, float)
     c = np.array([(sz[0] - 1) / 2.0, (sz[1] - 1) / 2.0])
-    Hs = [_homography(obj[:, :2], im) for im in imgs]
+    Hs = _homographies(obj[:, :2], imgs)
     # cvInitIntrinsicParams2D: with the principal point removed, each homography gives two
     # linear equations in (1/frow^2, 1/fcol^2)
     A, b = [], []
