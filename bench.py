@@ -38,6 +38,9 @@ WORKLOADS = {
     "c2": dict(sz=(1080, 1920), frames=64, u8=False, bytes_per_px=8,
                intr=(1400.0, 1400.0, 540.0, 960.0, -0.12, 1.0), seed=1234,
                name="64 x 1080x1920 fp32 gray frames, full-frame rectification (BASELINE configs[1])"),
+    "c4k": dict(sz=(2160, 3840), frames=16, u8=False, bytes_per_px=8,
+                intr=(2800.0, 2800.0, 1080.0, 1920.0, -0.12, 1.0), seed=1234,
+                name="16 x 2160x3840 fp32 gray frames, full-frame rectification (4K variant of configs[1])"),
     "c3": dict(sz=(2160, 3840), frames=16, u8=True, bytes_per_px=6,
                intr=(2800.0, 2800.0, 1080.0, 1920.0, -0.12, 1.0), seed=4321,
                name="16 x 2160x3840 u8 RGB frames per step (ring slice of BASELINE configs[2])"),
@@ -377,7 +380,7 @@ def extras(cc, torch, dev, c2cal, args):
     peak, _ = measured_peak()
     ex = {}
     # the other variants of the rectification kernels
-    for wname in ("c2", "c3"):
+    for wname in ("c2", "c4k", "c3"):
         wl = WORKLOADS[wname]
         sz, nfr = wl["sz"], wl["frames"]
         cal = cc.Calibration(wl["intr"][:4], [BENCH_VIEW], 1.0, wl["intr"][4], ["extrinsic.png"])
