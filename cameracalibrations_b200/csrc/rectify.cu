@@ -223,6 +223,8 @@ struct RectPlan {
     std::vector<double> q2;        // exact path: second-axis world term of every output line
     TileHdr* d_hdr;
     double* d_q2;
+    int per_sm[2];                 // resident CTAs per SM of the staged kernel, [exact], cached (0: not queried yet)
+    size_t per_sm_smem[2];
 };
 
 static void plan_free(RectPlan* p) {
@@ -354,6 +356,7 @@ static RectPlan* plan_get(cc_ctx* ctx, const ChainD& ch, double ratio, const Rec
     RectPlan* p = new (std::nothrow) RectPlan();
     if (!p) return nullptr;
     p->key = key; p->d_hdr = nullptr; p->d_q2 = nullptr;
+    p->per_sm[0] = p->per_sm[1] = 0; p->per_sm_smem[0] = p->per_sm_smem[1] = 0;
     plan_footprints(p);
     plan_boxes(p);
     if (!p->hdr.empty()) {
@@ -466,10 +469,17 @@ void rectify_free_sched(cc_ctx* ctx) {
 
 // persistent grid of a staged kernel: every CTA slot of the device (tickets do the balancing)
 template <typename K>
-static int persistent_grid(cc_ctx* ctx, K kernel, size_t smem, const TileCfg& cfg, uint32_t* gsz) {
-    int rc = set_smem(kernel, smem), per_sm = 0;
-    if (rc) return rc;
-    CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kConsumerThreads + 32, smem));
+static int persistent_grid(cc_ctx* ctx, K kernel, size_t smem, const TileCfg& cfg, RectPlan* plan, bool exact,
+                           uint32_t* gsz) {
+    // the occupancy query and the shared-memory attribute cost microseconds per call: once per plan
+    int per_sm = plan->per_sm_smem[exact] == smem ? plan->per_sm[exact] : 0;
+    if (per_sm == 0) {
+        int rc = set_smem(kernel, smem);
+        if (rc) return rc;
+        CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kConsumerThreads + 32, smem));
+        plan->per_sm[exact] = per_sm;
+        plan->per_sm_smem[exact] = smem;
+    }
     if (const char* e = getenv("CAMCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // tuning knob
     *gsz = std::min<uint32_t>(cfg.units, (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1));
     if (getenv("CAMCAL_DEBUG"))
@@ -528,8 +538,8 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
-        if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, &gsz)
-                        : persistent_grid(ctx, rectify_f32c1_kernel<false>, smem, cfg, &gsz))) return rc;
+        if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)
+                        : persistent_grid(ctx, rectify_f32c1_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
         RectSched* sched = nullptr;
         if ((rc = sched_acquire(ctx, st, &sched))) return rc;
         if (exact)
@@ -578,8 +588,8 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
         // + 16: the word-granular gather may read the aligned words that hold the last tap bytes
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes + 16;
         uint32_t gsz = 0;
-        if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, &gsz)
-                        : persistent_grid(ctx, rectify_u8c3_kernel<false>, smem, cfg, &gsz))) return rc;
+        if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, plan, true, &gsz)
+                        : persistent_grid(ctx, rectify_u8c3_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
         RectSched* sched = nullptr;
         if ((rc = sched_acquire(ctx, st, &sched))) return rc;
         if (exact)
