@@ -14,14 +14,15 @@ const VIEW = (rvec = (0.05, -0.04, 0.02), tvec = (-9.3, -6.4, 30.0))
 const SZ = (1080, 1920)
 
 function calibration()
-    # the constructor of src/meta.jl:27-33 through the public helper of src/buildcalibrations.jl:1-6
-    CameraCalibrations.obj2img([collect(VIEW.rvec)], [collect(VIEW.tvec)], INTR.f, INTR.f, INTR.c..., 1.0),
-    INTR.k
+    # the constructor of src/meta.jl:27-33 through the helper of src/buildcalibrations.jl:1-6
+    intrinsic, extrinsics, scale = CameraCalibrations.obj2img([collect(VIEW.rvec)], [collect(VIEW.tvec)],
+                                                              INTR.f, INTR.f, INTR.c..., 1.0)
+    Calibration(intrinsic, extrinsics, scale, INTR.k, ["extrinsic.png"])
 end
 
 function main()
     nthreads, ncores = Threads.nthreads(), Sys.CPU_THREADS
-    c = Calibration(calibration()..., ["extrinsic.png"])
+    c = calibration()
     # --- point maps: threaded chunks of the broadcast the reference uses (src/buildcalibrations.jl:29,46)
     n = 2_000_000
     pts = [RowCol(SZ[1] * rand(), SZ[2] * rand()) for _ in 1:n]

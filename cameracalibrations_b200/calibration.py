@@ -190,9 +190,18 @@ def _default_device() -> int:
 # ---------------------------------------------------------------------------------
 # rectification of frames: src/plot_calibration.jl
 # ---------------------------------------------------------------------------------
-def get_ratio(imgpoints, checker_size) -> float:
-    """src/plot_calibration.jl:8-13.  imgpoints: (n1, n2, 2) array, [a, b] = corner (a, b)."""
+def get_ratio(imgpoints, checker_size, n_corners=None) -> float:
+    """src/plot_calibration.jl:8-13.  imgpoints: (n1, n2, 2) array, [a, b] = corner (a, b); or,
+    with n_corners = (n1, n2), the flat (n1*n2, 2) layout detect_fit returns (corner a fastest,
+    the memory of the reference's n1 x n2 Julia matrix)."""
     ip = np.asarray(imgpoints, dtype=np.float64)
+    if ip.ndim == 2:
+        if n_corners is None:
+            raise ValueError("flat (n1*n2, 2) image points need n_corners=(n1, n2)")
+        n1, n2 = int(n_corners[0]), int(n_corners[1])
+        if ip.shape != (n1 * n2, 2):
+            raise ValueError(f"expected {n1 * n2} corners, got array of shape {ip.shape}")
+        ip = ip.reshape(n2, n1, 2).transpose(1, 0, 2)
     n1, n2 = ip.shape[:2]
     rows = np.ascontiguousarray(ip[:, :, 0].T).ravel()
     cols = np.ascontiguousarray(ip[:, :, 1].T).ravel()
@@ -213,7 +222,7 @@ def get_axes(ratio, checker_size, n_corners, sz):
 def image_transformations(c: Calibration, extrinsic_index, imgpointss, checker_size, n_corners, sz):
     """src/plot_calibration.jl:15-22: (ratio, axs_min) that drive `warp`."""
     vi = c._index(extrinsic_index)
-    ratio = get_ratio(imgpointss[vi], checker_size)
+    ratio = get_ratio(imgpointss[vi], checker_size, n_corners)   # (n1, n2, 2) or detect_fit's flat layout
     return ratio, get_axes(ratio, checker_size, n_corners, sz)
 
 

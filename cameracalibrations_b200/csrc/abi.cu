@@ -60,11 +60,25 @@ static int check_params(const cc_ctx* ctx, const cc_intr* intr, const cc_view* v
     return CC_OK;
 }
 
-static int enter(cc_ctx* ctx) {
-    CC_REQUIRE(ctx != nullptr, "ctx is NULL");
-    CC_CUDA(cudaSetDevice(ctx->device));
-    return CC_OK;
-}
+// Every entry point runs on the context's device and leaves the CALLER's current device as it
+// found it (one process may drive several GPUs: a call on cuda:1 must not redirect the host's
+// later allocations).  `if ((rc = enter(ctx))) return rc;` declares the guard in the enclosing scope.
+struct DeviceGuard {
+    int prev = -1;
+    int set(cc_ctx* ctx) {
+        CC_REQUIRE(ctx != nullptr, "ctx is NULL");
+        int cur = -1;
+        CC_CUDA(cudaGetDevice(&cur));
+        if (cur != ctx->device) {
+            CC_CUDA(cudaSetDevice(ctx->device));
+            prev = cur;
+        }
+        return CC_OK;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define enter(ctx) _cc_guard.set(ctx)
+#define CC_GUARD DeviceGuard _cc_guard
 
 // ---- host pipeline ---------------------------------------------------------------
 static int ensure_slot(cc_ctx* ctx, int k, size_t in_bytes, size_t out_bytes) {
@@ -100,6 +114,7 @@ static int img2world_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* view,
     int rc = check_params(ctx, intr, view);
     if (rc) return rc;
     CC_REQUIRE(n == 0 || (row && col && x && y), "NULL point array");
+    CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
     build_chain(intr, view, &ch);
@@ -130,6 +145,7 @@ static int world2img_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* view,
     int rc = check_params(ctx, intr, view);
     if (rc) return rc;
     CC_REQUIRE(n == 0 || (row && col && x && y), "NULL point array");
+    CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
     build_chain(intr, view, &ch);
@@ -159,6 +175,7 @@ template <typename PX, typename LAUNCH>
 static int rectify_host(cc_ctx* ctx, const PX* src, PX* dst, int sz1, int sz2, size_t pitch,
                         size_t frame_stride, int nframes, size_t px_bytes, LAUNCH launch) {
     int rc;
+    CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     const size_t frame_elems = pitch * (size_t)sz2;          // device frames are stored pitch*sz2
     const size_t frame_bytes = frame_elems * px_bytes;
@@ -265,6 +282,7 @@ int cc_ctx_device(const cc_ctx* ctx, int* device) {
 }
 
 int cc_ctx_synchronize(cc_ctx* ctx) {
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     CC_CUDA(cudaDeviceSynchronize());
@@ -301,6 +319,7 @@ int cc_host_unregister(void* ptr) {
 #define CC_POINT_ENTRY(NAME, T, DIR)                                                              \
     int rc = check_params(ctx, intr, view);                                                       \
     if (rc) return rc;                                                                            \
+    CC_GUARD;                                                            \
     if ((rc = enter(ctx))) return rc;                                                             \
     ChainD ch;                                                                                    \
     build_chain(intr, view, &ch);
@@ -359,6 +378,7 @@ int cc_rectify_f32c1(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doub
     if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, frame_stride, nframes, ratio))) return rc;
     CC_REQUIRE(nframes == 0 || (src && dst), "NULL frame pointer");
     CC_REQUIRE(nframes == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
+    CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
     build_chain(intr, view, &ch);
@@ -376,6 +396,7 @@ int cc_rectify_u8c3(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doubl
     CC_REQUIRE(nframes == 0 || (src && dst), "NULL frame pointer");
     CC_REQUIRE(nframes == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
     CC_REQUIRE(fill != nullptr, "fill is NULL");
+    CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
     build_chain(intr, view, &ch);
@@ -429,6 +450,7 @@ int cc_rectify_map_f64(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, do
     if (rc) return rc;
     if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, pitch * (size_t)sz2, 1, ratio))) return rc;
     CC_REQUIRE(map_row && map_col, "NULL map pointer");
+    CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     ChainD ch;
     build_chain(intr, view, &ch);
@@ -480,6 +502,7 @@ int cc_reproj_jtj_f64(cc_ctx* ctx, const cc_intr* intr, double aspect, const cc_
     CC_REQUIRE(shared != nullptr, "shared is NULL");
     CC_REQUIRE(nviews == 0 || (views && obj && img && per_view), "NULL device pointer");
     CC_REQUIRE(intr->checker_size != 0.0, "checker_size must be non-zero");
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     return launch_reproj_jtj(ctx, intr, aspect, views, nviews, obj, img, ncorners, per_view, shared,
@@ -494,6 +517,7 @@ int cc_reproj_jtj_f64_host(cc_ctx* ctx, const cc_intr* intr, double aspect, cons
     CC_REQUIRE(shared != nullptr, "shared is NULL");
     CC_REQUIRE(nviews == 0 || (views && obj && img && per_view), "NULL host pointer");
     CC_REQUIRE(intr->checker_size != 0.0, "checker_size must be non-zero");
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     const size_t nv = (size_t)(nviews > 0 ? nviews : 1);
@@ -533,6 +557,7 @@ int cc_calculate_errors_f64(cc_ctx* ctx, const cc_intr* intr, const cc_view* vie
     CC_REQUIRE(nviews == 0 || (views && obj && img), "NULL device pointer");
     CC_REQUIRE(inverse_samples == 0 || (inv_rows && inv_cols), "NULL sample pointer");
     CC_REQUIRE(intr->checker_size != 0.0 && intr->frow != 0.0 && intr->fcol != 0.0, "bad intrinsics");
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     return launch_calc_errors(ctx, intr, views, nviews, obj, img, n1, n2, inv_rows, inv_cols,
@@ -546,6 +571,7 @@ int cc_lm_schur_f64(cc_ctx* ctx, const double* per_view, int nviews, double lamb
     CC_REQUIRE(nviews >= 0, "bad sizes");
     CC_REQUIRE(nviews == 0 || (per_view && yz), "NULL device pointer");
     CC_REQUIRE(lambda >= 0.0 && lambda == lambda, "lambda must be non-negative");
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     return launch_lm_schur(ctx, per_view, nviews, lambda, yz, schur, (cudaStream_t)stream);
@@ -559,6 +585,7 @@ int cc_lm_update_f64(cc_ctx* ctx, const double* shared, const double* schur, dou
     CC_REQUIRE(nviews == 0 || (yz && views_in && views_out), "NULL device pointer");
     CC_REQUIRE(lambda >= 0.0 && lambda == lambda, "lambda must be non-negative");
     CC_REQUIRE(free_mask != 0u && free_mask < 16u, "free_mask selects among the 4 shared parameters");
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     return launch_lm_update(ctx, shared, schur, lambda, free_mask, yz, views_in, nviews, views_out, delta,
@@ -573,6 +600,7 @@ int cc_lm_fit_f64_host(cc_ctx* ctx, cc_intr* intr, double aspect, unsigned free_
     CC_REQUIRE(free_mask != 0u && free_mask < 16u, "free_mask selects among the 4 shared parameters");
     CC_REQUIRE(max_iter >= 0 && eps >= 0.0, "bad stopping rule");
     CC_REQUIRE(aspect > 0.0 && intr->fcol != 0.0 && intr->checker_size != 0.0, "bad starting intrinsics");
+    CC_GUARD;
     int rc = enter(ctx);
     if (rc) return rc;
     return lm_fit_host(ctx, intr, aspect, free_mask, views, nviews, obj, img, ncorners, max_iter, eps, rms,

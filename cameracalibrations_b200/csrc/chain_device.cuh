@@ -60,9 +60,11 @@ __device__ __forceinline__ void world2img(const ChainF& ch, float x, float y, fl
 //                    reference still uses it): g convex decreasing left of it, Newton
 //                    from y0 = -max(2, sqrt(2/|c|)) ascends onto it
 // returns y = 1/x*.
-__device__ __forceinline__ float inv_radial_seed(float c) {
+// `three_real`: c >= -4/27, decided by the caller in ITS precision (the branch must not flip when
+// a double c just above -4/27 narrows to a float just below it: the result changes sign)
+__device__ __forceinline__ float inv_radial_seed(float c, bool three_real) {
     float y;
-    if (c >= -0.1481481f) {
+    if (three_real) {
         y = 1.0f;
     } else {
         y = -fmaxf(2.0f, sqrtf(__fdividef(2.0f, -c)));
@@ -104,7 +106,7 @@ __device__ __forceinline__ bool inv_radial_fixed(float c, float& y) {
 
 __device__ __forceinline__ float inv_radial_generic(float c) {
     if (c == 0.0f) return 1.0f;
-    float y = inv_radial_seed(c);
+    float y = inv_radial_seed(c, c >= -4.0f / 27.0f);
     // one more step at full FP32 accuracy
     const float t = y * y;
     const float g = fmaf(c * t, y, y - 1.0f);
@@ -124,7 +126,11 @@ __device__ __forceinline__ double inv_radial(double c) {
     // with an SFU reciprocal refined by one Newton-Schulz step: two polish steps give
     // e1 ~ K e0^2 + 2^-23 e0, e2 ~ K e1^2 + 1e-12 e1  -> full FP64 accuracy.
     float ys;
-    if (!inv_radial_fixed((float)c, ys)) ys = inv_radial_seed((float)c);     // rare
+    const float cf = (float)c;
+    const bool three_real = c >= -4.0 / 27.0;
+    if (!inv_radial_fixed(cf, ys))                                           // rare
+        // c within a float ulp above -4/27 narrows below it: no FP32 root to seed from, start at 1
+        ys = (three_real && !(cf >= -4.0f / 27.0f)) ? 1.0f : inv_radial_seed(cf, three_real);
     double y = (double)ys;
     const double c3 = 3.0 * c;
     double t = y * y;

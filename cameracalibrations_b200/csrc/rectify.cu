@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -53,6 +54,10 @@ constexpr int kTLu = CAMCAL_TL_U8;     // u8c3: lines per tile
 #endif
 constexpr int kFloorMode1 = CAMCAL_FLOOR1, kFloorMode2 = CAMCAL_FLOOR2;
 constexpr int kMaxStages = 4;
+#ifndef CAMCAL_PITCH_ALIGN
+#define CAMCAL_PITCH_ALIGN 128
+#endif
+constexpr int kPitchAlign = CAMCAL_PITCH_ALIGN;   // staged line pitch granularity in bytes (16: dense boxes, tuning only)
 #ifndef CAMCAL_PRODUCER_SLEEP
 #define CAMCAL_PRODUCER_SLEEP 256
 #endif
@@ -69,13 +74,14 @@ constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
 #define CAMCAL_MINB_U8 1
 #endif
 #ifndef CAMCAL_MINB_U8_EXACT
-#define CAMCAL_MINB_U8_EXACT 4
+#define CAMCAL_MINB_U8_EXACT 3
 #endif
 constexpr int kMinBlocksU8 = CAMCAL_MINB_U8, kMinBlocksU8Exact = CAMCAL_MINB_U8_EXACT;
 constexpr int kConsumerThreads = 32 * kWarps;
 
 struct TileCfg {
     int box1, box2;        // staged box, in pixels (box1 along the contiguous axis)
+    int pitch_b;           // bytes between consecutive lines of a staged box (multiple of 128, see plan_boxes)
     int stages;
     int ntiles2;           // tiles along the second axis
     int box_bytes;         // bytes one TMA load delivers = stage stride (multiple of 128)
@@ -217,6 +223,7 @@ struct RectPlan {
     int n1, n2;                    // tiles along the first / second axis
     int need1, need2;              // largest footprint (pixels), incl. taps and slack
     int box1, box2, box_bytes;     // staged box (pixels) and its size; box_bytes == 0: not stageable
+    int pitch_b;                   // bytes per staged line
     std::vector<int> origin;       // per tile: floor(min row), floor(min col) of the perimeter samples
     std::vector<unsigned char> p3_ok;
     std::vector<TileHdr> hdr;      // tile headers
@@ -310,10 +317,16 @@ static void plan_boxes(RectPlan* p) {
     const int unit = (pxb == 4) ? 4 : 16;
     // (+ unit - 1: the box origin is rounded down to a multiple of `unit` pixels)
     p->box1 = (p->need1 + unit - 1 + unit - 1) / unit * unit;
+    // Line pitch of the staged box: a multiple of 128 bytes (all 32 banks).  The lanes of a warp read
+    // consecutive texels, but on a rotated map part of the warp samples source line i2 and the rest
+    // line i2+1; with any other pitch the second group lands on banks the first one uses (ncu, round 2:
+    // 1.7 wavefronts per LDS with 192-byte lines).  The extra columns cost shared memory, not DRAM traffic.
+    p->pitch_b = (p->box1 * pxb + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
+    p->box1 = p->pitch_b / pxb;                       // usable pixels per line
     p->box2 = p->need2;
-    while (((size_t)p->box1 * pxb * p->box2) % 128) ++p->box2;
-    const int box1_elems = (pxb == 4) ? p->box1 : p->box1 * 3;
-    p->box_bytes = p->box1 * pxb * p->box2;
+    while (((size_t)p->pitch_b * p->box2) % 128) ++p->box2;
+    const int box1_elems = (pxb == 4) ? p->pitch_b / 4 : p->pitch_b;
+    p->box_bytes = p->pitch_b * p->box2;
     if (box1_elems > 256 || p->box2 > 256 || p->box_bytes > 40 * 1024) p->box_bytes = 0;   // not worth staging
     if (!p->box_bytes) return;
     p->hdr.resize((size_t)p->n1 * p->n2);
@@ -334,7 +347,7 @@ static void plan_boxes(RectPlan* p) {
         h.Mk2 = 4503599627370496.0 - (double)k2;
         h.mk1 = 12582912.0f - (float)k1;
         h.mk2 = 12582912.0f - (float)k2;
-        h.base_off = (uint32_t)(lo2 * p->box1 + lo1) * (uint32_t)pxb;
+        h.base_off = (uint32_t)lo2 * (uint32_t)p->pitch_b + (uint32_t)lo1 * (uint32_t)pxb;
     }
     p->q2.resize((size_t)g.sz2);
     const double inv_ratio = 1.0 / p->key.ratio;
@@ -413,7 +426,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
     while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 
-    const int box1_elems = (pxb == 4) ? plan->box1 : plan->box1 * 3;
+    const int box1_elems = (pxb == 4) ? plan->pitch_b / 4 : plan->pitch_b;
     cuuint64_t dims[3] = {(cuuint64_t)g.sz1 * (pxb == 4 ? 1 : 3), (cuuint64_t)g.sz2,
                           (cuuint64_t)std::max(g.nframes, 1)};
     cuuint64_t strides[2] = {(cuuint64_t)pitch_b, (cuuint64_t)(g.nframes > 1 ? frame_b : pitch_b * g.sz2)};
@@ -425,14 +438,26 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     cfg->box1 = plan->box1; cfg->box2 = plan->box2; cfg->stages = stages; cfg->box_bytes = plan->box_bytes;
+    cfg->pitch_b = plan->pitch_b;
     *plan_out = plan;
     return true;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the KERNEL (per device), not to a plan:
+// the library remembers the largest value it has set per staged kernel and device and only ever
+// raises it (a smaller plan must not lower the limit under a cached larger one, whichever context
+// of the process made either call).
+static std::mutex g_smem_mu;
+static size_t g_smem_attr[64][4];
 template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-    if (bytes > 32 * 1024)     // static smem (barriers + headers) counts against the 48 KB default too
+static int set_smem(cc_ctx* ctx, int kslot, K kernel, size_t bytes) {
+    if (bytes <= 32 * 1024) return CC_OK;     // static smem (barriers + headers) counts against the 48 KB default too
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t& cur = g_smem_attr[ctx->device & 63][kslot];
+    if (bytes > cur) {
         CC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
     return CC_OK;
 }
 
@@ -469,13 +494,13 @@ void rectify_free_sched(cc_ctx* ctx) {
 
 // persistent grid of a staged kernel: every CTA slot of the device (tickets do the balancing)
 template <typename K>
-static int persistent_grid(cc_ctx* ctx, K kernel, size_t smem, const TileCfg& cfg, RectPlan* plan, bool exact,
+static int persistent_grid(cc_ctx* ctx, int kslot, K kernel, size_t smem, const TileCfg& cfg, RectPlan* plan, bool exact,
                            uint32_t* gsz) {
     // the occupancy query and the shared-memory attribute cost microseconds per call: once per plan
+    int rc = set_smem(ctx, kslot, kernel, smem);
+    if (rc) return rc;
     int per_sm = plan->per_sm_smem[exact] == smem ? plan->per_sm[exact] : 0;
     if (per_sm == 0) {
-        int rc = set_smem(kernel, smem);
-        if (rc) return rc;
         CC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kConsumerThreads + 32, smem));
         plan->per_sm[exact] = per_sm;
         plan->per_sm_smem[exact] = smem;
@@ -483,8 +508,8 @@ static int persistent_grid(cc_ctx* ctx, K kernel, size_t smem, const TileCfg& cf
     if (const char* e = getenv("CAMCAL_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // tuning knob
     *gsz = std::min<uint32_t>(cfg.units, (uint32_t)ctx->sm_count * (uint32_t)std::max(per_sm, 1));
     if (getenv("CAMCAL_DEBUG"))
-        fprintf(stderr, "[camcal] staged: box %dx%d (%d B) stages %d units %u (fg %d) grid %u (%d/SM) smem %zu\n",
-                cfg.box1, cfg.box2, cfg.box_bytes, cfg.stages, cfg.units, cfg.fg, *gsz, per_sm, smem);
+        fprintf(stderr, "[camcal] staged: box %dx%d pitch %d (%d B) stages %d units %u (fg %d) grid %u (%d/SM) smem %zu\n",
+                cfg.box1, cfg.box2, cfg.pitch_b, cfg.box_bytes, cfg.stages, cfg.units, cfg.fg, *gsz, per_sm, smem);
     return CC_OK;
 }
 
@@ -538,8 +563,8 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
-        if ((rc = exact ? persistent_grid(ctx, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)
-                        : persistent_grid(ctx, rectify_f32c1_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
+        if ((rc = exact ? persistent_grid(ctx, 0, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)
+                        : persistent_grid(ctx, 1, rectify_f32c1_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
         RectSched* sched = nullptr;
         if ((rc = sched_acquire(ctx, st, &sched))) return rc;
         if (exact)
@@ -588,8 +613,8 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
         // + 16: the word-granular gather may read the aligned words that hold the last tap bytes
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes + 16;
         uint32_t gsz = 0;
-        if ((rc = exact ? persistent_grid(ctx, rectify_u8c3_kernel<true>, smem, cfg, plan, true, &gsz)
-                        : persistent_grid(ctx, rectify_u8c3_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
+        if ((rc = exact ? persistent_grid(ctx, 2, rectify_u8c3_kernel<true>, smem, cfg, plan, true, &gsz)
+                        : persistent_grid(ctx, 3, rectify_u8c3_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
         RectSched* sched = nullptr;
         if ((rc = sched_acquire(ctx, st, &sched))) return rc;
         if (exact)

@@ -118,7 +118,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
     // ---- consumer warps
     const unsigned pitch = (unsigned)g.pitch;
-    const uint32_t box_pitch_b = (uint32_t)cfg.box1 * 4u;
+    const uint32_t box_pitch_b = (uint32_t)cfg.pitch_b;
     const uint32_t stage0 = smem_u32(stage_mem);
 
     // the map of the current unit

@@ -27,6 +27,16 @@ __device__ __forceinline__ void ring_init(SmemRing* ring, int stages) {
     __syncthreads();
 }
 
+// CAMCAL_PRODUCER_PARK > 0: wait with the barrier's own suspend-time hint (the polling loop of
+// try_wait + nanosleep was 8 % of all executed warp instructions of the u8 kernel, ncu round 2)
+#ifndef CAMCAL_PRODUCER_PARK
+#define CAMCAL_PRODUCER_PARK 2000
+#endif
+__device__ __forceinline__ void producer_wait(uint64_t* bar, uint32_t parity) {
+    if (CAMCAL_PRODUCER_PARK > 0) mbar_wait_parked<CAMCAL_PRODUCER_PARK>(bar, parity);
+    else mbar_wait<kProducerSleep>(bar, parity);
+}
+
 __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
     uint32_t u = 0;
     if (lane_id == 0) u = atomicAdd(&sched->next, 1u);
@@ -66,7 +76,7 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const Rec
         u_next = take_ticket(sched, lane_id);
         const int x0 = __shfl_sync(0xffffffffu, (int)hword, 8), y0 = __shfl_sync(0xffffffffu, (int)hword, 9);
         for (int f = f0; f < f1; ++f) {
-            mbar_wait<kProducerSleep>(&ring->empty[s], phase);
+            producer_wait(&ring->empty[s], phase);
             if (f == f0) {                                        // the map inputs travel with the first frame
                 if (lane_id < 12) reinterpret_cast<uint32_t*>(&ring->hdr[s])[lane_id] = hword;
                 if (EXACT) {
@@ -84,7 +94,7 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const Rec
         }
     }
     // stop marker
-    mbar_wait<kProducerSleep>(&ring->empty[s], phase);
+    producer_wait(&ring->empty[s], phase);
     if (lane_id == 0) { ring->pos[s] = make_int4(0, 0, -1, 0); mbar_arrive(&ring->full[s]); }
     // every producer has taken its last ticket before it counts itself out
     if (lane_id == 0 && atomicAdd(&sched->done, 1u) == gridDim.x - 1) {

@@ -36,16 +36,15 @@ __device__ __forceinline__ Taps6 load6(const uint32_t* words, unsigned o, unsign
 }
 __device__ __forceinline__ unsigned sel6(unsigned o) { return 0x3210u + 0x1111u * (o & 3u); }
 
+// Shared-memory loads as ordinary C++ loads (not volatile asm): the compiler is free to hoist the
+// loads of the next pixels above the arithmetic and the stores of the current ones; the "memory"
+// clobber of the mbarrier wait/arrive keeps them inside one stage's lifetime.
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
+    return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(addr));
 }
 template <int OFF>
 __device__ __forceinline__ uint32_t lds_u32_off(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    return v;
+    return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(addr + OFF));
 }
 // six bytes out of the three words at word-aligned shared address wa
 __device__ __forceinline__ Taps6 lds6w(uint32_t wa, unsigned sel) {
@@ -204,21 +203,157 @@ rectify_u8c3_direct_kernel(const __grid_constant__ RectExact pe, const __grid_co
 }
 
 // ---- staged kernel (persistent; scheduling and producer: rectify_ring.cuh) ------------------
-// Same unit structure as rectify_f32c1_kernel: the map of a tile (tap byte offset, weights, pixel
-// class) is built once per group of frames and kept in registers (8 pixels per lane); every
-// frame then only gathers, blends and stores.  Both coordinate variants blend in FP32 from FP32
-// copies of the weights; the exact variant certifies each rounding and, for the rare pixel that
-// fails, recomputes the FP64 weights and blends in FP64 (oracle order).
-template <bool EXACT>
+// Same unit structure as rectify_f32c1_kernel: the map of a tile is built once per group of frames
+// and kept in registers (8 pixels per lane); every frame then only gathers, blends and stores.
+//
+// Per pixel the map is the byte offset of tap (0,0) inside a stage and the FOUR bilinear weights
+//   w00 = (1-d1)(1-d2), w10 = d1(1-d2), w01 = (1-d1)d2, w11 = d1 d2          (a_xy: x = first axis)
+// as FP32 numbers scaled by 2^100, for pairs of lines (FFMA2 lanes).  A tap byte's bit pattern is
+// the denormal float b * 2^-149, so one FMUL2 and three FFMA2 per channel and pair of pixels give
+// v * 2^-49 with no unpacking arithmetic at all, and the FFMA2 by 2^49 onto 2^23 leaves rint(v) in
+// the low byte (v >= 0: weights and taps are non-negative).
+//
+// Exact variant: weights are the FP64 products rounded to FP32.  Error of the FP32 blend against
+// the FP64 blend of the oracle:
+//   four roundings of partial sums < 256 (half an ulp = 7.63e-6 each)            3.05e-5
+//   representation of the weights (relative 2^-24, sum of w_i b_i <= 255)        1.52e-5
+// so |v32 - v64| <= 4.6e-5 LSB, and whenever v32 is farther than 6.5e-5 from a rounding boundary
+// rint(v32) == rint(v64).  Every lane keeps max |v32 - rint(v32)| per pixel; once per frame the
+// warp votes, and the pixels that are closer (1.3e-4 of the values; exact .5 ties included) are
+// re-blended in FP64 in the oracle's operation order and patched with byte stores.  The output is
+// bit-identical to the FP64 blend.
+//
+// Tap bytes: CAMCAL_U8_LOAD 1 reads every tap byte with LDS.U8 (no ALU work; the load unit
+// isolates the byte), 0 reads three aligned words per source line and isolates bytes with PRMT.
+//
+// Stores: the 32 pixels of a warp's line are 96 contiguous bytes = 24 words.  Lane L (L % 4 != 3)
+// builds word L - L/4 from its own packed pixel and lane L+1's (one shuffle, one PRMT).
+#ifndef CAMCAL_U8_LOAD
+#define CAMCAL_U8_LOAD 3
+#endif
+#ifndef CAMCAL_U8_DEBUG
+#define CAMCAL_U8_DEBUG 0
+#endif
+constexpr int kU8Load = CAMCAL_U8_LOAD;
+constexpr bool kU8Bytes = CAMCAL_U8_LOAD == 1;      // rel[] is a byte address (no word alignment / selector)
+constexpr bool kU8Mixed = CAMCAL_U8_LOAD >= 3;   // words for line i2, bytes for (part of) line i2+1
+constexpr float kMagic23 = 8388608.0f;                 // 2^23: rint(v) in the low mantissa byte, low 24 bits of the pattern zero
+
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u8_off(uint32_t addr) {
+    return *reinterpret_cast<const uint8_t*>(__cvta_shared_to_generic(addr + OFF));
+}
+
+// predicated streaming store (no branch around it)
+__device__ __forceinline__ void stcs_if(bool p, uint32_t* q, uint32_t v) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.cs.u32 [%1], %2; }" :: "r"((uint32_t)p), "l"(q), "r"(v));
+}
+
+// the 12 tap bytes of one pixel as denormal-float bit patterns: [c] a00, [3+c] a10, [6+c] a01, [9+c] a11
+struct TapF { uint32_t m[12]; };
+
+// A0: shared address of tap (0,0) of source line i2 (byte address when kU8Load, else rounded down
+// to a word with `sel` funnelling the bytes); A1: the same on line i2+1
+__device__ __forceinline__ TapF load_taps(uint32_t A0, uint32_t A1, unsigned sel, uint32_t A1b = 0) {
+    TapF t;
+    if (kU8Load == 1) {
+        t.m[0] = lds_u8_off<0>(A0); t.m[1] = lds_u8_off<1>(A0); t.m[2] = lds_u8_off<2>(A0);
+        t.m[3] = lds_u8_off<3>(A0); t.m[4] = lds_u8_off<4>(A0); t.m[5] = lds_u8_off<5>(A0);
+        t.m[6] = lds_u8_off<0>(A1); t.m[7] = lds_u8_off<1>(A1); t.m[8] = lds_u8_off<2>(A1);
+        t.m[9] = lds_u8_off<3>(A1); t.m[10] = lds_u8_off<4>(A1); t.m[11] = lds_u8_off<5>(A1);
+    } else if (kU8Load == 3) {
+        // source line i2: three aligned words + PRMT (ALU pipe); line i2+1: six LDS.U8 (load unit)
+        const Taps6 r0 = lds6w(A0, sel);
+        t.m[0] = __byte_perm(r0.lo, 0u, 0x4440); t.m[1] = __byte_perm(r0.lo, 0u, 0x4441); t.m[2] = __byte_perm(r0.lo, 0u, 0x4442);
+        t.m[3] = __byte_perm(r0.lo, 0u, 0x4443); t.m[4] = __byte_perm(r0.hi, 0u, 0x4440); t.m[5] = __byte_perm(r0.hi, 0u, 0x4441);
+        t.m[6] = lds_u8_off<0>(A1b); t.m[7] = lds_u8_off<1>(A1b); t.m[8] = lds_u8_off<2>(A1b);
+        t.m[9] = lds_u8_off<3>(A1b); t.m[10] = lds_u8_off<4>(A1b); t.m[11] = lds_u8_off<5>(A1b);
+    } else if (kU8Load == 5) {
+        // as 3, with half of line i2's bytes isolated on the FMA pipe (IDP.4A with a one-hot vector)
+        const Taps6 r0 = lds6w(A0, sel);
+        t.m[0] = __dp4a(r0.lo, 0x00000001u, 0u); t.m[1] = __byte_perm(r0.lo, 0u, 0x4441); t.m[2] = __dp4a(r0.lo, 0x00010000u, 0u);
+        t.m[3] = __byte_perm(r0.lo, 0u, 0x4443); t.m[4] = __dp4a(r0.hi, 0x00000001u, 0u); t.m[5] = __byte_perm(r0.hi, 0u, 0x4441);
+        t.m[6] = lds_u8_off<0>(A1b); t.m[7] = lds_u8_off<1>(A1b); t.m[8] = lds_u8_off<2>(A1b);
+        t.m[9] = lds_u8_off<3>(A1b); t.m[10] = lds_u8_off<4>(A1b); t.m[11] = lds_u8_off<5>(A1b);
+    } else if (kU8Load == 4) {
+        // as 3, but only tap a11 (three bytes) through LDS.U8; a01 from two aligned words
+        const Taps6 r0 = lds6w(A0, sel);
+        const uint32_t r1lo = __byte_perm(lds_u32(A1), lds_u32_off<4>(A1), sel);
+        t.m[0] = __byte_perm(r0.lo, 0u, 0x4440); t.m[1] = __byte_perm(r0.lo, 0u, 0x4441); t.m[2] = __byte_perm(r0.lo, 0u, 0x4442);
+        t.m[3] = __byte_perm(r0.lo, 0u, 0x4443); t.m[4] = __byte_perm(r0.hi, 0u, 0x4440); t.m[5] = __byte_perm(r0.hi, 0u, 0x4441);
+        t.m[6] = __byte_perm(r1lo, 0u, 0x4440); t.m[7] = __byte_perm(r1lo, 0u, 0x4441); t.m[8] = __byte_perm(r1lo, 0u, 0x4442);
+        t.m[9] = lds_u8_off<3>(A1b); t.m[10] = lds_u8_off<4>(A1b); t.m[11] = lds_u8_off<5>(A1b);
+    } else if (kU8Load == 2) {
+        // half of the bytes isolated on the FMA pipe (IDP.4A with a one-hot byte vector), half with PRMT (ALU pipe)
+        const Taps6 r0 = lds6w(A0, sel), r1 = lds6w(A1, sel);
+        t.m[0] = __dp4a(r0.lo, 0x00000001u, 0u); t.m[1] = __byte_perm(r0.lo, 0u, 0x4441); t.m[2] = __dp4a(r0.lo, 0x00010000u, 0u);
+        t.m[3] = __byte_perm(r0.lo, 0u, 0x4443); t.m[4] = __dp4a(r0.hi, 0x00000001u, 0u); t.m[5] = __byte_perm(r0.hi, 0u, 0x4441);
+        t.m[6] = __dp4a(r1.lo, 0x00000001u, 0u); t.m[7] = __byte_perm(r1.lo, 0u, 0x4441); t.m[8] = __dp4a(r1.lo, 0x00010000u, 0u);
+        t.m[9] = __byte_perm(r1.lo, 0u, 0x4443); t.m[10] = __dp4a(r1.hi, 0x00000001u, 0u); t.m[11] = __byte_perm(r1.hi, 0u, 0x4441);
+    } else {
+        const Taps6 r0 = lds6w(A0, sel), r1 = lds6w(A1, sel);
+        t.m[0] = __byte_perm(r0.lo, 0u, 0x4440); t.m[1] = __byte_perm(r0.lo, 0u, 0x4441); t.m[2] = __byte_perm(r0.lo, 0u, 0x4442);
+        t.m[3] = __byte_perm(r0.lo, 0u, 0x4443); t.m[4] = __byte_perm(r0.hi, 0u, 0x4440); t.m[5] = __byte_perm(r0.hi, 0u, 0x4441);
+        t.m[6] = __byte_perm(r1.lo, 0u, 0x4440); t.m[7] = __byte_perm(r1.lo, 0u, 0x4441); t.m[8] = __byte_perm(r1.lo, 0u, 0x4442);
+        t.m[9] = __byte_perm(r1.lo, 0u, 0x4443); t.m[10] = __byte_perm(r1.hi, 0u, 0x4440); t.m[11] = __byte_perm(r1.hi, 0u, 0x4441);
+    }
+    return t;
+}
+__device__ __forceinline__ float2 tap2(const TapF& p, const TapF& q, int k) {
+    return make_float2(__uint_as_float(p.m[k]), __uint_as_float(q.m[k]));
+}
+
+// one channel of two pixels: scaled blend, rounding, and (CERT) the distance from the rounded value
+template <bool CERT>
+__device__ __forceinline__ float2 blend_ch2(const TapF& p, const TapF& q, int c, float2 w00, float2 w10,
+                                            float2 w01, float2 w11, float2& dist) {
+    float2 acc = mul2(w00, tap2(p, q, c));
+    acc = fma2(w10, tap2(p, q, 3 + c), acc);
+    acc = fma2(w01, tap2(p, q, 6 + c), acc);
+    acc = fma2(w11, tap2(p, q, 9 + c), acc);
+    const float2 f = fma2(acc, bc2(kTwo49), bc2(kMagic23));
+    if (CERT) dist = fma2(acc, bc2(-kTwo49), add2(f, bc2(-kMagic23)));       // rint(v) - v, exact
+    return f;
+}
+__device__ __forceinline__ uint32_t pack_rgb(float fr, float fg, float fb) {
+    // patterns are 0x4B000000 + value: the multiples of 2^8 and 2^16 of 0x4B000000 vanish mod 2^32
+    return __float_as_uint(fr) + (__float_as_uint(fg) << 8) + (__float_as_uint(fb) << 16);
+}
+__device__ __forceinline__ float max_abs3(float a, float b, float c) { return fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c)); }
+
+// two pixels (lines e, e+1 of a lane): packed 0x..BBGGRR each; CERT: max |v - rint(v)| per pixel
+template <bool CERT>
+__device__ __forceinline__ void blend_px2(const TapF& p, const TapF& q, float2 w00, float2 w10, float2 w01,
+                                          float2 w11, uint32_t& rgb_p, uint32_t& rgb_q, float2& dmax) {
+    float2 dr, dg, db;
+    const float2 fr = blend_ch2<CERT>(p, q, 0, w00, w10, w01, w11, dr);
+    const float2 fg = blend_ch2<CERT>(p, q, 1, w00, w10, w01, w11, dg);
+    const float2 fb = blend_ch2<CERT>(p, q, 2, w00, w10, w01, w11, db);
+    rgb_p = pack_rgb(fr.x, fg.x, fb.x);
+    rgb_q = pack_rgb(fr.y, fg.y, fb.y);
+    if (CERT) dmax = make_float2(max_abs3(dr.x, dg.x, db.x), max_abs3(dr.y, dg.y, db.y));
+}
+
+// FP64 blend of one pixel in the oracle's operation order (taps re-read from the stage)
 __device__ __noinline__ uint32_t reblend_exact_u8(const RectExact* pe, const RectGeom* g, int a, int b,
-                                                  const Taps6 t0, const Taps6 t1) {
+                                                  uint32_t A0, uint32_t A1) {
     const RowTermD rtd = rect_row_term(*pe, g->axs0 + a);
     double row, col, d1, d2;
     int i1, i2;
     rect_coord(*pe, rtd, rect_q2(*pe, g->axs1 + b), row, col);
     lin_floor(row, i1, d1);
     lin_floor(col, i2, d2);
-    return blend_rgb<true>(t0, t1, d1, d2, 0.f, 0.f);
+    uint32_t t[12];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[k]) : "r"(A0 + k));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[6 + k]) : "r"(A1 + k));
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        out |= (uint32_t)(int)rint(bilerp((double)t[c], (double)t[3 + c], (double)t[6 + c], (double)t[9 + c], d1, d2)) << (8 * c);
+    return out;
 }
 
 template <bool EXACT>
@@ -229,10 +364,10 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     const double* __restrict__ q2tab, RectSched* __restrict__ sched,
                     const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
                     unsigned frame_bytes) {
-    constexpr int KB = 4;                         // pixels blended together (two packed pairs)
     constexpr int TL = kTLu;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
-    static_assert(LPW % KB == 0 && LPW <= 16, "batches of four lines; masks are 16 bits");
+    constexpr int NP = LPW / 2;                   // pairs of lines
+    static_assert(LPW % 2 == 0 && LPW <= 16, "pairs of lines; masks are 16 bits");
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemRing ring;
     const int lane_id = threadIdx.x & 31;
@@ -246,18 +381,19 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 
     // ---- consumer warps
     const unsigned pitch3 = (unsigned)g.pitch * 3u;
-    const uint32_t box_pitch_b = (uint32_t)cfg.box1 * 3u;      // bytes per box line (multiple of 48)
+    const uint32_t box_pitch_b = (uint32_t)cfg.pitch_b;       // bytes per box line (multiple of 128)
     const uint32_t stage0 = smem_u32(stage_mem);
     const uint32_t fill = fill3.x | (fill3.y << 8) | (fill3.z << 16);
-    // store transpose: output word L (< 24) of a line holds bytes 4L..4L+3 = pixels p0, p0+1
-    const int wp0 = min((4 * lane_id) / 3, 31), wo = (4 * lane_id) % 3;
-    const unsigned wsel = wo == 0 ? 0x4210u : (wo == 1 ? 0x5421u : 0x6542u);
-    const int wp1 = min(wp0 + 1, 31);
+    // store: lane L (L % 4 != 3) writes word L - L/4 of the line = own pixel's tail + next pixel's head
+    const int lq = lane_id & 3;
+    const unsigned wsel = lq == 0 ? 0x4210u : (lq == 1 ? 0x5421u : 0x6542u);
+    const int widx = lane_id - (lane_id >> 2);
 
     // the map of the current unit
-    uint32_t rel[LPW];                                 // first tap's byte offset inside a stage, rounded down to a word
-    uint32_t selv[LPW];                                // PRMT selector that funnels the 6 tap bytes out of 3 words
-    float2 wf1[LPW / 2], wf2[LPW / 2];                 // weights, pairs of lines (FP32 copies when EXACT)
+    uint32_t rel[LPW];                                 // tap (0,0) offset inside a stage (bytes; word-aligned when !kU8Load)
+    [[maybe_unused]] uint32_t selv[LPW];               // !kU8Load: PRMT selector that funnels the 6 tap bytes out of 3 words
+    [[maybe_unused]] uint32_t relb[LPW];               // kU8Mixed: the unrounded byte offset
+    float2 w00[NP], w10[NP], w01[NP], w11[NP];         // weights * 2^100, pairs of lines
     uint32_t m_staged = 0, m_fill = 0, m_skip = 0;
     bool all_staged = false;
     int a = 0, b0 = 0;
@@ -288,6 +424,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 const RowTermD rtd = rect_row_term(pe, g.axs0 + a_c);
                 const double Mk1 = h->Mk1, Mk2 = h->Mk2;
                 const double* q2p = &ring.q2[s][warp * LPW];
+                const double up = 1.2676506002282294e30;      // 2^100
 #pragma unroll
                 for (int e = 0; e < LPW; ++e) {
                     double row, col, d1, d2;
@@ -297,10 +434,13 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     floor_index<kFloorMode2>(col, Mk2, t2, h2, d2);
                     const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 3u;
-                    selv[e] = sel6(rel[e]);            // stages are 128-byte aligned: (address & 3) == (rel & 3)
-                    rel[e] &= ~3u;
-                    if (e & 1) { wf1[e / 2].y = (float)d1; wf2[e / 2].y = (float)d2; }
-                    else       { wf1[e / 2].x = (float)d1; wf2[e / 2].x = (float)d2; }
+                    if (kU8Mixed) relb[e] = rel[e];
+                    if (!kU8Bytes) { selv[e] = sel6(rel[e]); rel[e] &= ~3u; }   // stages are 128-byte aligned: (address & 3) == (rel & 3)
+                    const double e1 = 1.0 - d1, e2 = 1.0 - d2;
+                    const float v00 = (float)((e1 * e2) * up), v10 = (float)((d1 * e2) * up);
+                    const float v01 = (float)((e1 * d2) * up), v11 = (float)((d1 * d2) * up);
+                    if (e & 1) { w00[e / 2].y = v00; w10[e / 2].y = v10; w01[e / 2].y = v01; w11[e / 2].y = v11; }
+                    else       { w00[e / 2].x = v00; w10[e / 2].x = v10; w01[e / 2].x = v01; w11[e / 2].x = v11; }
                     if (st) m_staged |= 1u << e;
                     else if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) m_fill |= 1u << e;   // rare: border tiles
                 }
@@ -311,13 +451,17 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 ip.x = (float)(g.axs1 + b0) - pf.c2;
                 ip.y = ip.x + 1.0f;
 #pragma unroll
-                for (int hh = 0; hh < LPW / 2; ++hh) {
-                    float2 row, col;
+                for (int hh = 0; hh < NP; ++hh) {
+                    float2 row, col, d1, d2;
                     rect_coord2(pf, rtf, ip, row, col);
                     ip = add2(ip, bc2(2.0f));
                     uint32_t t1[2], t2[2];
-                    floor_bits_fast2(row, mk1, t1[0], t1[1], wf1[hh]);
-                    floor_bits_fast2(col, mk2, t2[0], t2[1], wf2[hh]);
+                    floor_bits_fast2(row, mk1, t1[0], t1[1], d1);
+                    floor_bits_fast2(col, mk2, t2[0], t2[1], d2);
+                    const float2 e1 = sub2(bc2(1.0f), d1), e2 = mul2(sub2(bc2(1.0f), d2), bc2(kTwo100));
+                    const float2 d2s = mul2(d2, bc2(kTwo100));
+                    w00[hh] = mul2(e1, e2); w10[hh] = mul2(d1, e2);
+                    w01[hh] = mul2(e1, d2s); w11[hh] = mul2(d1, d2s);
                     const float rr[2] = {row.x, row.y}, cc_[2] = {col.x, col.y};
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
@@ -325,8 +469,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                         const uint32_t l1 = t1[j] - (uint32_t)kMagicBits, l2 = t2[j] - (uint32_t)kMagicBits;
                         const bool st = (l1 < R1) & (l2 < R2);
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 3u;
-                        selv[e] = sel6(rel[e]);
-                        rel[e] &= ~3u;
+                        if (kU8Mixed) relb[e] = rel[e];
+                        if (!kU8Bytes) { selv[e] = sel6(rel[e]); rel[e] &= ~3u; }
                         // (unconditional: four FSETPs cost less than a divergent branch here; measured)
                         const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         if (st) m_staged |= 1u << e;
@@ -343,44 +487,57 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         const uint8_t* sframe = src + (long long)pos.z * g.frame_stride * 3;
         uint8_t* oline = dst + (long long)pos.z * g.frame_stride * 3 + off0;
         const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+        const uint32_t sbase1 = sbase + box_pitch_b;
         if (all_staged) {
-            uint32_t* ow = reinterpret_cast<uint32_t*>(oline) + lane_id;
+            uint32_t* ow = reinterpret_cast<uint32_t*>(oline) + widx;
+            [[maybe_unused]] float2 dm[NP];
 #pragma unroll
-            for (int bt = 0; bt < LPW / KB; ++bt) {
-                uint32_t rgb[KB];
-                [[maybe_unused]] bool amb[KB];
-                Taps6 ta[KB], tb[KB];
-#pragma unroll
-                for (int j = 0; j < KB; ++j) {
-                    const uint32_t o = sbase + rel[bt * KB + j];       // word aligned
-#ifdef CAMCAL_CHECK_BOUNDS      // debug builds: the three words of both lines inside the stage
-                    if (o < sbase || o + box_pitch_b + 12u > sbase + (uint32_t)cfg.box_bytes + 4u || (o & 3u)) __trap();
+            for (int hh = 0; hh < NP; ++hh) {
+                const int e = 2 * hh;
+#ifdef CAMCAL_CHECK_BOUNDS      // debug builds: every tap byte of both lines inside the stage
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t o = sbase + rel[e + j];
+                    if (o < sbase || o + box_pitch_b + (kU8Bytes ? 6u : 12u) > sbase + (uint32_t)cfg.box_bytes + 4u || (!kU8Bytes && (o & 3u))) __trap();
+                }
 #endif
-                    const unsigned sel = selv[bt * KB + j];    // box_pitch_b % 4 == 0: same for both lines
-                    ta[j] = lds6w(o, sel);
-                    tb[j] = lds6w(o + box_pitch_b, sel);
-                }
+                const TapF tp = load_taps(sbase + rel[e], sbase1 + rel[e], kU8Bytes ? 0u : selv[e], kU8Mixed ? sbase1 + relb[e] : 0u);
+                const TapF tq = load_taps(sbase + rel[e + 1], sbase1 + rel[e + 1], kU8Bytes ? 0u : selv[e + 1], kU8Mixed ? sbase1 + relb[e + 1] : 0u);
+                uint32_t rgb_p, rgb_q;
+#if CAMCAL_U8_DEBUG == 1        // tuning only: no unpack / blend (pipeline + store floor)
+                rgb_p = tp.m[0] ^ tp.m[7]; rgb_q = tq.m[0] ^ tq.m[7];
+                if (EXACT) dm[hh] = make_float2(0.f, 0.f);
+#else
+                blend_px2<EXACT>(tp, tq, w00[hh], w10[hh], w01[hh], w11[hh], rgb_p, rgb_q, dm[hh]);
+#endif
+                const uint32_t np_ = __shfl_down_sync(0xffffffffu, rgb_p, 1);
+                const uint32_t nq_ = __shfl_down_sync(0xffffffffu, rgb_q, 1);
+#if CAMCAL_U8_DEBUG == 2        // tuning only: compute everything, (almost) never store
+                const bool st_ok = (lq != 3) & (rgb_p == 0x12345678u);
+#else
+                const bool st_ok = lq != 3;
+#endif
+                stcs_if(st_ok, ow, __byte_perm(rgb_p, np_, wsel));
+                stcs_if(st_ok, reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ow) + pitch3), __byte_perm(rgb_q, nq_, wsel));
+                ow = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ow) + 2 * pitch3);
+            }
+            if (EXACT) {
+                float mx = 0.0f;
 #pragma unroll
-                for (int hh = 0; hh < KB / 2; ++hh)
-                    blend_rgb2<EXACT>(ta[2 * hh], tb[2 * hh], ta[2 * hh + 1], tb[2 * hh + 1],
-                                      wf1[bt * (KB / 2) + hh], wf2[bt * (KB / 2) + hh],
-                                      rgb[2 * hh], rgb[2 * hh + 1], amb[2 * hh], amb[2 * hh + 1]);
-                if (EXACT) {
-                    bool any = false;
+                for (int hh = 0; hh < NP; ++hh) mx = fmaxf(mx, fmaxf(dm[hh].x, dm[hh].y));
+                if (__any_sync(0xffffffffu, mx > kCertThr)) {      // rare: certify by the FP64 blend, patch the bytes
+                    __syncwarp();                                  // the word stores above are ordered before the patches
 #pragma unroll
-                    for (int j = 0; j < KB; ++j) any |= amb[j];
-                    if (__any_sync(0xffffffffu, any)) {        // rare: certify by the FP64 blend
+                    for (int hh = 0; hh < NP; ++hh) {
 #pragma unroll
-                        for (int j = 0; j < KB; ++j)
-                            if (amb[j]) rgb[j] = reblend_exact_u8<true>(&pe, &g, a, b0 + bt * KB + j, ta[j], tb[j]);
+                        for (int j = 0; j < 2; ++j) {
+                            const int e = 2 * hh + j;
+                            if ((j ? dm[hh].y : dm[hh].x) > kCertThr) {
+                                const uint32_t bo = rel[e] + (kU8Bytes ? 0u : (selv[e] & 3u));
+                                store_rgb(oline + (long long)e * pitch3 + lane_id * 3,
+                                          reblend_exact_u8(&pe, &g, a, b0 + e, sbase + bo, sbase1 + bo));
+                            }
+                        }
                     }
-                }
-#pragma unroll
-                for (int j = 0; j < KB; ++j) {
-                    const uint32_t v0 = __shfl_sync(0xffffffffu, rgb[j], wp0);
-                    const uint32_t v1 = __shfl_sync(0xffffffffu, rgb[j], wp1);
-                    if (lane_id < 24) __stcs(ow, __byte_perm(v0, v1, wsel));
-                    ow = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ow) + pitch3);
                 }
             }
         } else {
@@ -392,21 +549,23 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 uint32_t v;
                 if ((m_staged >> e) & 1u) {
                     uint32_t r = 0, sel = 0;
-                    float f1 = 0, f2 = 0;
+                    float f00 = 0, f10 = 0, f01 = 0, f11 = 0;
 #pragma unroll
                     for (int j = 0; j < LPW; ++j)
                         if (j == e) {
                             r = rel[j];
-                            sel = selv[j];
-                            f1 = (j & 1) ? wf1[j / 2].y : wf1[j / 2].x;
-                            f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x;
+                            if (!kU8Bytes) sel = selv[j];
+                            f00 = (j & 1) ? w00[j / 2].y : w00[j / 2].x; f10 = (j & 1) ? w10[j / 2].y : w10[j / 2].x;
+                            f01 = (j & 1) ? w01[j / 2].y : w01[j / 2].x; f11 = (j & 1) ? w11[j / 2].y : w11[j / 2].x;
                         }
-                    const uint32_t q = sbase + r;
-                    const Taps6 t0 = lds6w(q, sel), t1 = lds6w(q + box_pitch_b, sel);
+                    const TapF t = load_taps(sbase + r, sbase1 + r, sel, sbase1 + r + (sel & 3u));
                     uint32_t vq;
-                    bool am, amq;
-                    blend_rgb2<EXACT>(t0, t1, t0, t1, make_float2(f1, f1), make_float2(f2, f2), v, vq, am, amq);
-                    if (EXACT && am) v = reblend_exact_u8<true>(&pe, &g, a, b0 + e, t0, t1);
+                    float2 dm1;
+                    blend_px2<EXACT>(t, t, bc2(f00), bc2(f10), bc2(f01), bc2(f11), v, vq, dm1);
+                    if (EXACT && dm1.x > kCertThr) {
+                        const uint32_t bo = r + (kU8Bytes ? 0u : (sel & 3u));
+                        v = reblend_exact_u8(&pe, &g, a, b0 + e, sbase + bo, sbase1 + bo);
+                    }
                 } else if ((m_fill >> e) & 1u) {
                     v = fill;
                 } else {

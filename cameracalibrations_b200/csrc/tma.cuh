@@ -36,6 +36,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the warp for up to `ns` (no instructions
+// issued meanwhile) and wakes it when the phase completes.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return done != 0;
+}
+// producer side: long parked waits (a free stage appears once per item, microseconds apart)
+template <int HINT_NS>
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait_hint(bar, parity, HINT_NS)) {}
+}
 // Polling costs issue slots that other CTAs on the SM could use: back off between probes.
 #ifndef CAMCAL_WAIT_SLEEP
 #define CAMCAL_WAIT_SLEEP 256

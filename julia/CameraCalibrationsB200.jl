@@ -56,7 +56,16 @@ mutable struct Context
     end
 end
 const CTX = Ref{Union{Nothing,Context}}(nothing)
-context() = something(CTX[], (CTX[] = Context(0)))
+# one context per process, created on first use (`something(a, b)` would evaluate b -- a NEW
+# context -- on every call, leaking device buffers and discarding the cached rectification plans)
+function context()
+    ctx = CTX[]
+    if ctx === nothing
+        ctx = Context(0)
+        CTX[] = ctx
+    end
+    ctx
+end
 
 # ---- batch pixel -> world: bulk form of c.(imgpoints, i), src/buildcalibrations.jl:46 --------
 """

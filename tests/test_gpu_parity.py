@@ -127,6 +127,16 @@ def test_inverse_distortion_branches(cc):
     assert np.max(np.abs(x.cpu().numpy() - ox)[~near]) <= TOL64
     assert np.max(np.abs(x.cpu().numpy() - ox)[near]) <= 1e-6
     assert np.all(x.cpu().numpy()[cneg > 0.1485] < 0)      # the reference divides by the negative root
+    # c within a FLOAT ulp of -4/27 on either side: the branch (three real roots / one negative
+    # root) is decided in the input precision, so the sign of the result follows the oracle's
+    edge = 4.0 / 27.0 + np.array([-1e-8, -3e-9, -1e-10, 1e-10, 3e-9, 1e-8])
+    row = np.sqrt(edge)
+    x, y, z = c.img2world(_dev(row), _dev(np.zeros_like(row)), 0)
+    ox, oy, oz = oc.img2world_soa(oc.chain(intr, *view), row, np.zeros_like(row))
+    cedge = row * row                                      # what the chain actually sees
+    assert np.array_equal(np.sign(x.cpu().numpy()), np.sign(ox))
+    assert np.all(ox[cedge < 4.0 / 27.0 - 1e-12] > 0) and np.all(ox[cedge > 4.0 / 27.0 + 1e-12] < 0)
+    assert np.max(np.abs(x.cpu().numpy() - ox)) <= 1e-3   # ill-conditioned at the double root: ~sqrt(distance)
 
 
 def test_f32_fast_path_round_trip(cc):
@@ -360,6 +370,29 @@ def test_rectify_plan_cache_many_parameter_sets(cc):
                 got2 = cc.warp(c, i, fd, ratio, axs, fill=-3.0, coord="f64")
             side.synchronize()
             assert np.array_equal(got2.cpu().numpy(), refs[i]), i
+
+
+def test_rectify_alternating_large_and_small_boxes(cc):
+    """A plan whose staged ring needs more than the 48 KB default of dynamic shared memory, then one
+    that does not, then the first again from the plan cache: the kernel's shared-memory limit must
+    only ever be raised (it belongs to the kernel, not to the plan).  Both pixel formats."""
+    sz = (512, 384)
+    intr = camera_for(sz)
+    rng = np.random.default_rng(17)
+    frames = rng.random((2, sz[1], sz[0]), dtype=np.float32)
+    f8 = rng.integers(0, 256, (2, sz[1], sz[0], 3), dtype=np.uint8)
+    c = _calib(cc, intr, [SYN_VIEW])
+    cases = [_rect_case(intr, sz, ratio_scale=s) for s in (0.42, 1.0)]
+    refs = [(oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-4.0), oc.rectify_u8c3(ch, 1.0 / ratio, axs, f8))
+            for ch, _, ratio, axs in cases]
+    for i in (0, 1, 0, 1, 0):
+        _, _, ratio, axs = cases[i]
+        for coord in ("f64", "f32"):
+            got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=-4.0, gather="tma", coord=coord).cpu().numpy()
+            got8 = cc.warp(c, 0, _dev(f8), ratio, axs, coord=coord).cpu().numpy()   # (a u8 box is capped at 256 B per line)
+            if coord == "f64":
+                assert np.array_equal(got, refs[i][0]), i
+                assert np.array_equal(got8, refs[i][1]), i
 
 
 @pytest.mark.parametrize("pad1,padf", [(4, 64), (3, 7), (0, 16)])
