@@ -32,6 +32,7 @@ SHARED = 21
 LM_YZ = 30
 LM_SCHUR = 21
 LM_DELTA = 8
+COMM_ID_BYTES = 128
 
 
 class CamcalError(RuntimeError):
@@ -94,6 +95,15 @@ _SIGS = {
     "cc_lm_schur_f64": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
     "cc_lm_update_f64": (_i, [_vp, _vp, _vp, _d, _u, _vp, _vp, _i, _vp, _vp, _vp]),
     "cc_lm_fit_f64_host": (_i, [_vp, _pI, _d, _u, _vp, _i, _vp, _vp, _i, _i, _d, C.POINTER(_d), C.POINTER(_i)]),
+    "cc_lm_fit_f64": (_i, [_vp, _pI, _d, _u, _vp, _i, _vp, _vp, _i, _i, _d, C.POINTER(_d), C.POINTER(_i), _vp]),
+    "cc_lm_initial_guess_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _pI, _vp, _vp]),
+    "cc_comm_unique_id": (_i, [_vp]),
+    "cc_comm_init_rank": (_i, [_vp, _i, _i, _vp]),
+    "cc_comm_destroy": (_i, [_vp]),
+    "cc_comm_size": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "cc_comm_nccl_version": (_i, [C.POINTER(_i)]),
+    "cc_allreduce_shared": (_i, [_vp, _vp, _sz, _vp]),
+    "cc_ctx_collective_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -145,6 +155,44 @@ class Context:
         check(lib.cc_ctx_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def collective_count(self) -> int:
+        n = C.c_uint64()
+        check(lib.cc_ctx_collective_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    # -- NCCL communicator of this context (csrc/comm.cu) ------------------------------------
+    def comm_size(self):
+        n, r = _i(1), _i(0)
+        check(lib.cc_comm_size(self._h, C.byref(n), C.byref(r)))
+        return int(n.value), int(r.value)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes | None):
+        """cc_comm_init_rank: `unique_id` = the 128 bytes rank 0 got from comm_unique_id()."""
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES) if unique_id is not None else None
+        check(lib.cc_comm_init_rank(self._h, int(nranks), int(rank), buf))
+
+    def comm_init_from_torch(self, group=None):
+        """Bootstrap over an initialised torch.distributed group (any backend): rank 0 creates the
+        NCCL unique id, the group broadcasts its 128 bytes, every rank joins.  torch only carries
+        the id; the all-reduces of the hot path then run inside libcamcal_b200 on raw NCCL."""
+        import torch.distributed as dist
+        if self.comm_size()[0] > 1:
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            return
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(world, rank, box[0])
+
+    def allreduce(self, t):
+        """in-place sum of a float64 CUDA tensor over the ranks (cc_allreduce_shared), torch's current stream"""
+        import torch
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        st = C.c_void_p(torch.cuda.current_stream(t.device.index).cuda_stream)
+        check(lib.cc_allreduce_shared(self._h, C.c_void_p(t.data_ptr()), C.c_size_t(t.numel()), st))
+        return t
+
     def close(self):
         if getattr(self, "_h", None):
             lib.cc_ctx_destroy(self._h)
@@ -165,6 +213,12 @@ def context(device: int = 0) -> Context:
     if ctx is None:
         ctx = _contexts[device] = Context(device)
     return ctx
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(lib.cc_comm_unique_id(buf))
+    return buf.raw
 
 
 def device_count() -> int:

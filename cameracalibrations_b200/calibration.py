@@ -306,6 +306,23 @@ def views_tensor(extrinsics, device):
     return torch.from_numpy(a).to(device)
 
 
+def _dist_world(group=None) -> int:
+    d = torch.distributed if torch is not None else None
+    return d.get_world_size(group) if d is not None and d.is_available() and d.is_initialized() else 1
+
+
+def allreduce_shared(t, group=None):
+    """The exchange step of the path: in-place sum of a small float64 CUDA tensor over the ranks,
+    through cc_allreduce_shared (raw NCCL inside libcamcal_b200, csrc/comm.cu).  torch.distributed
+    is only the bootstrap that carries the NCCL unique id to the other ranks, once per context."""
+    if _dist_world(group) > 1:
+        dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        ctx = _lib.context(dev)
+        ctx.comm_init_from_torch(group)
+        ctx.allreduce(t)
+    return t
+
+
 def reproj_jtj(intr, aspect, views, obj, img, group=None):
     """Residual sum, Jacobian and normal-equation blocks of this rank's views.
 
@@ -313,7 +330,7 @@ def reproj_jtj(intr, aspect, views, obj, img, group=None):
     obj: (ncorners, 3); img: (nviews, ncorners, 2).  numpy -> host entry point; CUDA torch
     tensors -> device entry point.  Returns (per_view (nviews, 66), shared (21,)).
     With torch.distributed initialised (or `group` given) the shared block is all-reduced
-    (NCCL sum) so every rank holds the global J'J_ii, J'r_i and sum r^2.
+    (NCCL sum through cc_allreduce_shared) so every rank holds the global J'J_ii, J'r_i and sum r^2.
     """
     ci = _lib.make_intr(*[float(v) for v in intr])
     if _is_torch(img):
@@ -327,8 +344,7 @@ def reproj_jtj(intr, aspect, views, obj, img, group=None):
         check(lib.cc_reproj_jtj_f64(_lib.context(dev).handle, C.byref(ci), float(aspect), _t_ptr(views),
                                     nv, _t_ptr(obj), _t_ptr(img), nc, _t_ptr(pv), _t_ptr(sh),
                                     _stream_ptr(dev)))
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(sh, group=group)
+        allreduce_shared(sh, group)
         return pv, sh
     views = np.ascontiguousarray(views, dtype=np.float64).reshape(-1, 6)
     obj = np.ascontiguousarray(obj, dtype=np.float64)
@@ -366,11 +382,10 @@ def calculate_errors(c: Calibration, imgpointss, objpoints, checker_size, sz, fi
                                       _t_ptr(obj), _t_ptr(img), n1, n2, _t_ptr(ir), _t_ptr(ic),
                                       int(inverse_samples), _t_ptr(sums), _stream_ptr(dev)))
     n_files = nv
-    if torch.distributed.is_available() and torch.distributed.is_initialized():
-        cnt = torch.tensor([float(nv)], dtype=torch.float64, device=device)
-        torch.distributed.all_reduce(sums, group=group)
-        torch.distributed.all_reduce(cnt, group=group)
-        n_files = int(cnt.item())
+    if _dist_world(group) > 1:                      # one all-reduce: the four sums and the view count
+        both = torch.cat([sums, torch.tensor([float(nv)], dtype=torch.float64, device=device)])
+        allreduce_shared(both, group)
+        sums, n_files = both[:4], int(round(float(both[4].item())))
     s = sums.cpu().numpy()
     n = n1 * n2 * n_files
     return dict(n=n_files,

@@ -50,6 +50,10 @@ int lm_fit_host(cc_ctx*, cc_intr*, double, unsigned, cc_view*, int, const double
                 double*, int*);
 int launch_lm_update(cc_ctx*, const double*, const double*, double, unsigned, const double*, const cc_view*,
                      int, cc_view*, double*, cudaStream_t);
+int lm_fit_device(cc_ctx*, cc_intr*, double, unsigned, cc_view*, int, const double*, const double*, int, int, double,
+                  double*, int*, cudaStream_t);
+int launch_initial_guess(cc_ctx*, const double*, const double*, int, int, int, int, double, cc_intr*, cc_view*,
+                         cudaStream_t);
 
 static int check_params(const cc_ctx* ctx, const cc_intr* intr, const cc_view* view) {
     CC_REQUIRE(ctx != nullptr, "ctx is NULL");
@@ -269,6 +273,8 @@ int cc_ctx_destroy(cc_ctx* ctx) {
         if (ctx->pipe_out[k]) cudaFree(ctx->pipe_out[k]);
     }
     if (ctx->jtj_scratch) cudaFree(ctx->jtj_scratch);
+    lm_free_workspace(ctx);
+    comm_free(ctx);
     rectify_free_plans(ctx);
     rectify_free_sched(ctx);
     delete ctx;
@@ -605,6 +611,39 @@ int cc_lm_fit_f64_host(cc_ctx* ctx, cc_intr* intr, double aspect, unsigned free_
     if (rc) return rc;
     return lm_fit_host(ctx, intr, aspect, free_mask, views, nviews, obj, img, ncorners, max_iter, eps, rms,
                        iterations);
+}
+
+int cc_lm_fit_f64(cc_ctx* ctx, cc_intr* intr, double aspect, unsigned free_mask, cc_view* views, int nviews,
+                  const double* obj, const double* img, int ncorners, int max_iter, double eps, double* rms,
+                  int* iterations, void* stream) {
+    CC_REQUIRE(ctx && intr && obj, "NULL argument");
+    CC_REQUIRE(nviews >= 0 && ncorners > 0, "bad sizes");
+    CC_REQUIRE(nviews == 0 || (views && img), "NULL view / image-point array");
+    CC_REQUIRE(free_mask != 0u && free_mask < 16u, "free_mask selects among the 4 shared parameters");
+    CC_REQUIRE(max_iter >= 0 && eps >= 0.0, "bad stopping rule");
+    CC_REQUIRE(aspect > 0.0 && intr->fcol != 0.0 && intr->checker_size != 0.0, "bad starting intrinsics");
+    CC_GUARD;
+    int rc = enter(ctx);
+    if (rc) return rc;
+    return lm_fit_device(ctx, intr, aspect, free_mask, views, nviews, obj, img, ncorners, max_iter, eps, rms,
+                         iterations, (cudaStream_t)stream);
+}
+
+int cc_lm_initial_guess_f64(cc_ctx* ctx, const double* obj, const double* img, int nviews, int ncorners, int sz1,
+                            int sz2, double aspect, cc_intr* intr, cc_view* views, void* stream) {
+    CC_REQUIRE(ctx && intr && obj, "NULL argument");
+    CC_REQUIRE(nviews >= 0 && ncorners >= 4 && sz1 > 0 && sz2 > 0, "bad sizes (a homography needs >= 4 corners)");
+    CC_REQUIRE(nviews == 0 || (views && img), "NULL view / image-point array");
+    CC_GUARD;
+    int rc = enter(ctx);
+    if (rc) return rc;
+    return launch_initial_guess(ctx, obj, img, nviews, ncorners, sz1, sz2, aspect, intr, views, (cudaStream_t)stream);
+}
+
+int cc_ctx_collective_count(const cc_ctx* ctx, uint64_t* count) {
+    CC_REQUIRE(ctx && count, "NULL argument");
+    *count = ctx->collectives;
+    return CC_OK;
 }
 
 }  // extern "C"

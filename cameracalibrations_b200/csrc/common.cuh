@@ -28,6 +28,8 @@ void build_chain(const cc_intr* in, const cc_view* vw, ChainD* out);
 void narrow_chain(const ChainD& d, ChainF* f);
 void rectify_free_plans(struct ::cc_ctx* ctx);
 void rectify_free_sched(struct ::cc_ctx* ctx);
+void comm_free(struct ::cc_ctx* ctx);
+void lm_free_workspace(struct ::cc_ctx* ctx);
 
 // error plumbing (abi.cu)
 int set_error(int status, const char* fmt, ...);
@@ -63,6 +65,12 @@ struct cc_ctx {
     cudaStream_t sched_stream[NSCHED];
     unsigned char sched_used[NSCHED];
     unsigned sched_next;
+    // NCCL communicator of this context (comm.cu); NULL / 1 rank: a world of one
+    void* nccl_comm;
+    int comm_nranks, comm_rank;
+    unsigned long long collectives;       // all-reduces issued so far
+    // workspace of the device-resident LM loop (lm.cu: LmWorkspace), grown on demand
+    void* lm_ws;
 };
 
 #define CC_CUDA(call)                                                     \

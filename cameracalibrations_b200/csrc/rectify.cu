@@ -54,10 +54,13 @@ constexpr int kTLu = CAMCAL_TL_U8;     // u8c3: lines per tile
 #endif
 constexpr int kFloorMode1 = CAMCAL_FLOOR1, kFloorMode2 = CAMCAL_FLOOR2;
 constexpr int kMaxStages = 4;
-#ifndef CAMCAL_PITCH_ALIGN
-#define CAMCAL_PITCH_ALIGN 128
+// staged line pitch granularity in bytes, per pixel format (16: dense boxes; 128: all 32 banks, see plan_boxes)
+#ifndef CAMCAL_PITCH_ALIGN_U8
+#define CAMCAL_PITCH_ALIGN_U8 128
 #endif
-constexpr int kPitchAlign = CAMCAL_PITCH_ALIGN;   // staged line pitch granularity in bytes (16: dense boxes, tuning only)
+#ifndef CAMCAL_PITCH_ALIGN_F32
+#define CAMCAL_PITCH_ALIGN_F32 16
+#endif
 #ifndef CAMCAL_PRODUCER_SLEEP
 #define CAMCAL_PRODUCER_SLEEP 256
 #endif
@@ -317,11 +320,14 @@ static void plan_boxes(RectPlan* p) {
     const int unit = (pxb == 4) ? 4 : 16;
     // (+ unit - 1: the box origin is rounded down to a multiple of `unit` pixels)
     p->box1 = (p->need1 + unit - 1 + unit - 1) / unit * unit;
-    // Line pitch of the staged box: a multiple of 128 bytes (all 32 banks).  The lanes of a warp read
+    // Line pitch of the staged u8 box: a multiple of 128 bytes (all 32 banks).  The lanes of a warp read
     // consecutive texels, but on a rotated map part of the warp samples source line i2 and the rest
     // line i2+1; with any other pitch the second group lands on banks the first one uses (ncu, round 2:
-    // 1.7 wavefronts per LDS with 192-byte lines).  The extra columns cost shared memory, not DRAM traffic.
-    p->pitch_b = (p->box1 * pxb + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
+    // 1.7 wavefronts per LDS with 192-byte lines, which made the byte loads of the u8 kernel the bound).
+    // The extra columns cost shared memory and L2->SM traffic, not DRAM traffic.  The f32 kernels are
+    // not bound by the shared-memory pipe and measured 3-4 % faster with dense boxes (more stages fit).
+    const int align = (pxb == 4) ? CAMCAL_PITCH_ALIGN_F32 : CAMCAL_PITCH_ALIGN_U8;
+    p->pitch_b = (p->box1 * pxb + align - 1) / align * align;
     p->box1 = p->pitch_b / pxb;                       // usable pixels per line
     p->box2 = p->need2;
     while (((size_t)p->pitch_b * p->box2) % 128) ++p->box2;

@@ -14,6 +14,7 @@
 // kernel in a fixed order (bit-reproducible; no atomics).  Across GPUs the 21 doubles
 // are all-reduced with NCCL by the host layer.
 #include "chain_device.cuh"
+#include "lm_state.cuh"
 
 namespace cc {
 
@@ -137,10 +138,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // acc layout: [0,21) JtJ_ee upper | [21,45) JtJ_ei | [45,51) Jtr_e | [51,61) JtJ_ii upper |
 //             [61,65) Jtr_i | [65] sse
-__global__ void __launch_bounds__(kResThreads)
-reproj_jtj_kernel(const SharedIntr in, const cc_view* __restrict__ views, int nviews,
-                  const double* __restrict__ obj, const double* __restrict__ img, int ncorners,
-                  double* __restrict__ per_view, double* __restrict__ scratch) {
+__device__ __forceinline__ void
+reproj_jtj_view(const SharedIntr& in, const cc_view* __restrict__ views, int nviews,
+                const double* __restrict__ obj, const double* __restrict__ img, int ncorners,
+                double* __restrict__ per_view, double* __restrict__ scratch) {
     const int lane_id = threadIdx.x & 31;
     const int view = blockIdx.x * kResWarps + (threadIdx.x >> 5);
     if (view >= nviews) return;
@@ -208,6 +209,47 @@ reproj_jtj_kernel(const SharedIntr in, const cc_view* __restrict__ views, int nv
         for (int i = 0; i < 4; ++i) scratch[(size_t)(16 + i) * nviews + view] = acc[61 + i];
         scratch[(size_t)20 * nviews + view] = acc[65];
     }
+}
+
+__global__ void __launch_bounds__(kResThreads)
+reproj_jtj_kernel(const SharedIntr in, const cc_view* __restrict__ views, int nviews,
+                  const double* __restrict__ obj, const double* __restrict__ img, int ncorners,
+                  double* __restrict__ per_view, double* __restrict__ scratch) {
+    reproj_jtj_view(in, views, nviews, obj, img, ncorners, per_view, scratch);
+}
+
+// The same blocks inside the device-resident LM loop (lm.cu): intrinsics and buffers come from
+// the loop state -- which == 0: current parameters and buffers; 1: the candidate of the last update.
+__global__ void __launch_bounds__(kResThreads)
+reproj_jtj_state_kernel(const LmState* __restrict__ st, int which, const LmBufs b, double aspect, double inv_cs,
+                        int nviews, const double* __restrict__ obj, const double* __restrict__ img,
+                        int ncorners, double* __restrict__ scratch) {
+    if (st->done) return;
+    const double* p = which ? st->cand : st->par;
+    const SharedIntr in{aspect * p[0], p[0], p[1], p[2], p[3], aspect, inv_cs};
+    const int slot = st->cur ^ which;
+    reproj_jtj_view(in, b.views[slot], nviews, obj, img, ncorners, b.pv[slot], scratch);
+}
+
+__device__ __forceinline__ void reduce_components(const double* __restrict__ scratch, int nviews,
+                                                  double* __restrict__ out) {
+    __shared__ double sm[256];
+    const double* col = scratch + (size_t)blockIdx.x * nviews;
+    double s = 0.0;
+    for (int v = threadIdx.x; v < nviews; v += 256) s += col[v];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(256)
+reduce_components_state_kernel(const LmState* __restrict__ st, const double* __restrict__ scratch, int nviews,
+                               double* __restrict__ out) {
+    if (st->done) return;
+    reduce_components(scratch, nviews, out);
 }
 
 // out[c] = sum_v scratch[c][v] in a fixed order: strided serial partials, then a tree
@@ -355,6 +397,23 @@ int launch_reproj_jtj(cc_ctx* ctx, const cc_intr* intr, double aspect, const cc_
         CC_CUDA(cudaGetLastError());
     }
     reduce_components_kernel<<<CC_SHARED, 256, 0, st>>>(ctx->jtj_scratch, nviews, shared);
+    ctx->launches++;
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_reproj_jtj_state(cc_ctx* ctx, const LmState* st, int which, const LmBufs& b, double aspect,
+                            double checker_size, int nviews, const double* obj, const double* img,
+                            int ncorners, double* shared_out, cudaStream_t stream) {
+    int rc = ensure_scratch(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1));
+    if (rc) return rc;
+    if (nviews > 0) {
+        reproj_jtj_state_kernel<<<(nviews + kResWarps - 1) / kResWarps, kResThreads, 0, stream>>>(
+            st, which, b, aspect, 1.0 / checker_size, nviews, obj, img, ncorners, ctx->jtj_scratch);
+        ctx->launches++;
+        CC_CUDA(cudaGetLastError());
+    }
+    reduce_components_state_kernel<<<CC_SHARED, 256, 0, stream>>>(st, ctx->jtj_scratch, nviews, shared_out);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
     return CC_OK;

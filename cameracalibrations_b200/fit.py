@@ -47,8 +47,8 @@ def fit_model(sz, objpoints, imgpointss, n_corners, with_distortion=True, aspect
     imgpointss = np.asarray(imgpointss, dtype=np.float64)
     if solver == "b200":
         from . import lm
-        intr0, views0 = lm.initial_guess(objpoints, imgpointss, sz, float(aspect))
-        r = lm.lm_fit(intr0, views0, objpoints, imgpointss, aspect=float(aspect), with_distortion=with_distortion)
+        intr0, views0 = lm.initial_guess_device(objpoints, imgpointss, sz, float(aspect))
+        r = lm.lm_fit_device(intr0, views0, objpoints, imgpointss, aspect=float(aspect), with_distortion=with_distortion)
         return dict(k=float(r["intr"][4]), Rs=[v[:3] for v in r["views"]], ts=[v[3:] for v in r["views"]],
                     frow=r["intr"][0], fcol=r["intr"][1], crow=r["intr"][2], ccol=r["intr"][3], rms=r["rms"])
     assert solver == "opencv", solver

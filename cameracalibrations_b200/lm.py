@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check, lib
-from .calibration import _t_ptr, _stream_ptr, reproj_jtj, torch
+from .calibration import _t_ptr, _stream_ptr, reproj_jtj, allreduce_shared, torch
 
 FREE_ALL = 0b1111
 FREE_NO_K = 0b0111          # CALIB_FIX_K1
@@ -160,7 +160,7 @@ def lm_fit(intr0, views0, obj, imgs, checker_size=1.0, aspect=1.0, with_distorti
     n_res = torch.tensor([1.0 * nv * nc], **f64)        # cv2 reports sqrt(sum |r|^2 / number of points)
     dist = _dist_on(group)
     if dist:
-        torch.distributed.all_reduce(n_res, group=group)
+        allreduce_shared(n_res, group)
     n_res = float(n_res.item())
     f, crow, ccol, k = float(intr0[1]), float(intr0[2]), float(intr0[3]), float(intr0[4])
     if not with_distortion:
@@ -177,10 +177,12 @@ def lm_fit(intr0, views0, obj, imgs, checker_size=1.0, aspect=1.0, with_distorti
         it += 1
         yz, schur = lm_schur(pv, lam)
         if dist:
-            torch.distributed.all_reduce(schur, group=group)
+            allreduce_shared(schur, group)
         cand, delta = lm_update(sh, schur, lam, mask, yz, views)
         if dist:
-            torch.distributed.all_reduce(delta[4:6], group=group)
+            norms = delta[4:6].clone()
+            allreduce_shared(norms, group)
+            delta[4:6] = norms
         d = delta.cpu().numpy()
         bad = float(schur[20].item()) > 0 or d[6] == 0.0 or not np.all(np.isfinite(d))
         if not bad:
@@ -202,6 +204,55 @@ def lm_fit(intr0, views0, obj, imgs, checker_size=1.0, aspect=1.0, with_distorti
             break
     return dict(intr=(aspect * f, f, crow, ccol, k), views=views.cpu().numpy(), rms=float(np.sqrt(sse / n_res)),
                 iterations=it, accepted=accepted, lam=lam, sse=sse)
+
+
+def lm_fit_device(intr0, views0, obj, imgs, checker_size=1.0, aspect=1.0, with_distortion=True, max_iter=30,
+                  eps=1e-3, device=None, group=None):
+    """cc_lm_fit_f64: the whole fit as ONE device-resident loop (csrc/lm.cu) over THIS rank's
+    views; damping, accept/reject and the stopping rule live in device memory, an iteration costs
+    two small NCCL all-reduces and no host synchronisation.  Same arguments and result as lm_fit;
+    device tensors may be passed for views0 / obj / imgs (views0 is then updated in place too)."""
+    assert torch is not None and torch.cuda.is_available(), "lm_fit_device runs on the GPU: no CPU fallback"
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    f64 = dict(dtype=torch.float64, device=dev)
+    as_t = lambda a: a.to(**f64).contiguous() if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, float), **f64).contiguous()
+    views = as_t(views0).reshape(-1, 6)
+    if views.data_ptr() == (views0.data_ptr() if torch.is_tensor(views0) else 0):
+        views = views.clone()
+    obj_t, img_t = as_t(obj), as_t(imgs)
+    nv, nc = int(views.shape[0]), int(obj_t.shape[0])
+    ctx = _lib.context(dev.index)
+    if _dist_on(group):
+        ctx.comm_init_from_torch(group)
+    ci = _lib.make_intr(aspect * intr0[1], intr0[1], intr0[2], intr0[3], intr0[4] if with_distortion else 0.0,
+                        checker_size)
+    rms, its = C.c_double(), C.c_int()
+    check(lib.cc_lm_fit_f64(ctx.handle, C.byref(ci), float(aspect), FREE_ALL if with_distortion else FREE_NO_K,
+                            _t_ptr(views), nv, _t_ptr(obj_t), _t_ptr(img_t), nc, int(max_iter), float(eps),
+                            C.byref(rms), C.byref(its), _stream_ptr(dev.index)))
+    return dict(intr=(ci.frow, ci.fcol, ci.crow, ci.ccol, ci.k), views=views.cpu().numpy(), views_device=views,
+                rms=rms.value, iterations=its.value)
+
+
+def initial_guess_device(obj, imgs, sz, aspect=1.0, device=None, group=None):
+    """cc_lm_initial_guess_f64: the starting values of initial_guess computed on the device for this
+    rank's views (batched DLT + pose kernels, csrc/init.cu).  Returns (intr 5-tuple, views (nv, 6)
+    CUDA tensor)."""
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    f64 = dict(dtype=torch.float64, device=dev)
+    as_t = lambda a: a.to(**f64).contiguous() if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, float), **f64).contiguous()
+    obj_t, img_t = as_t(obj), as_t(imgs)
+    nc = int(obj_t.shape[0])
+    img_t = img_t.reshape(-1, nc, 2)
+    nv = int(img_t.shape[0])
+    views = torch.empty((nv, 6), **f64)
+    ctx = _lib.context(dev.index)
+    if _dist_on(group):
+        ctx.comm_init_from_torch(group)
+    ci = _lib.make_intr(1.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+    check(lib.cc_lm_initial_guess_f64(ctx.handle, _t_ptr(obj_t), _t_ptr(img_t), nv, nc, int(sz[0]), int(sz[1]),
+                                      float(aspect), C.byref(ci), _t_ptr(views), _stream_ptr(dev.index)))
+    return (ci.frow, ci.fcol, ci.crow, ci.ccol, ci.k), views
 
 
 def lm_fit_host(intr0, views0, obj, imgs, checker_size=1.0, aspect=1.0, with_distortion=True, max_iter=30,

@@ -229,6 +229,45 @@ int cc_lm_update_f64(cc_ctx *ctx, const double *shared, const double *schur, dou
 int cc_lm_fit_f64_host(cc_ctx *ctx, cc_intr *intr, double aspect, unsigned free_mask,
                        cc_view *views, int nviews, const double *obj, const double *img,
                        int ncorners, int max_iter, double eps, double *rms, int *iterations);
+/* The same fit on DEVICE arrays, asynchronous on `stream` until the fitted intrinsics are handed
+ * back (one wait at the end), with THIS RANK'S views when the context has a communicator
+ * (cc_comm_init_rank): views/img hold the rank's shard, obj is replicated, intr goes in equal and
+ * comes out equal on every rank.  The loop state (damping, accept/reject, stopping rule) lives in
+ * device memory: an iteration costs two NCCL all-reduces (21 and 23 doubles) and NO host
+ * synchronisation.  nviews may be 0 on a rank.  rms counts the points of all ranks. */
+int cc_lm_fit_f64(cc_ctx *ctx, cc_intr *intr, double aspect, unsigned free_mask, cc_view *views,
+                  int nviews, const double *obj, const double *img, int ncorners, int max_iter,
+                  double eps, double *rms, int *iterations, void *stream);
+
+/* Starting values for cc_lm_fit_f64 from the detections alone, as calibrateCamera derives them
+ * inside the reference's fit (src/detect_fit.jl:34-36,47): principal point at the image centre,
+ * focal length from the homographies (cvInitIntrinsicParams2D, FIX_ASPECT_RATIO when aspect > 0),
+ * one pose per view from its homography; k = 0.  Device arrays (this rank's views); `views` is
+ * written, `intr` (host) gets frow, fcol, crow, ccol, k -- checker_size is left as passed in.
+ * obj must lie in the plane z = 0 (a checkerboard).  One stream wait (5 doubles come back). */
+int cc_lm_initial_guess_f64(cc_ctx *ctx, const double *obj, const double *img, int nviews,
+                            int ncorners, int sz1, int sz2, double aspect, cc_intr *intr,
+                            cc_view *views, void *stream);
+
+/* ---- multi-GPU: one process per GPU, one context per process, NCCL over NVLink for the small
+ *      shared blocks only (the reduction over views of src/buildcalibrations.jl:28-31,60-65 and
+ *      of the fit).  Frames, points and per-view blocks never cross GPUs.
+ *      Bootstrap: rank 0 calls cc_comm_unique_id and hands the 128 bytes to the other ranks by
+ *      any means (MPI, a file, torch.distributed); every rank then calls cc_comm_init_rank.
+ *      NCCL is resolved at run time: without libnccl.so.2 these return CC_ERR_UNSUPPORTED and
+ *      everything else still works.  A context without a communicator is a world of one, for
+ *      which cc_allreduce_shared is a no-op. */
+#define CC_COMM_ID_BYTES 128
+int cc_comm_unique_id(void *id128);
+int cc_comm_init_rank(cc_ctx *ctx, int nranks, int rank, const void *id128);
+int cc_comm_destroy(cc_ctx *ctx);
+int cc_comm_size(const cc_ctx *ctx, int *nranks, int *rank);
+int cc_comm_nccl_version(int *version);
+/* in-place sum of `count` doubles (device) over the ranks, asynchronous on `stream`:
+ * cc_reproj_jtj_f64's `shared`, cc_calculate_errors_f64's `sums`, cc_lm_schur_f64's `schur` */
+int cc_allreduce_shared(cc_ctx *ctx, double *buf, size_t count, void *stream);
+/* number of all-reduces this context has issued so far */
+int cc_ctx_collective_count(const cc_ctx *ctx, uint64_t *count);
 
 #ifdef __cplusplus
 }

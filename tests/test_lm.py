@@ -190,6 +190,56 @@ def test_lm_fit_without_distortion_and_many_views(cc):
     assert np.max(np.abs(r["views"] - views)) < 0.05
 
 
+@pytest.mark.gpu
+def test_lm_fit_device_loop_is_the_stepwise_loop(cc, example_fit):
+    """cc_lm_fit_f64 (device-resident state: damping, accept/reject and stopping rule decided by a
+    kernel, no host synchronisation per iteration) takes exactly the decisions of the stepwise
+    loop lm.lm_fit drives from the host: same iterations, same parameters bit for bit."""
+    from cameracalibrations_b200 import lm
+    obj, imgs = example_fit["obj_np"], example_fit["corners_np"]
+    intr0, views0 = lm.initial_guess(obj, imgs, example_fit["sz"], 1.0)
+    for kw in (dict(), dict(max_iter=60, eps=1e-10), dict(with_distortion=False), dict(max_iter=3), dict(max_iter=0)):
+        a = lm.lm_fit(intr0, views0, obj, imgs, **kw)
+        b = lm.lm_fit_device(intr0, views0, obj, imgs, **kw)
+        assert a["iterations"] == b["iterations"], kw
+        assert np.array_equal(np.asarray(a["intr"]), np.asarray(b["intr"])), kw
+        assert np.array_equal(a["views"], b["views"]) and a["rms"] == b["rms"], kw
+    # device tensors in, and a second call reuses the context's workspace
+    vt = torch.from_numpy(np.asarray(views0)).cuda()
+    c = lm.lm_fit_device(intr0, vt, torch.from_numpy(obj).cuda(), torch.from_numpy(imgs).cuda())
+    assert c["rms"] <= example_fit["cv2_rms"] + 1e-6 and c["views_device"].is_cuda
+    # a world of one: the collective of the ABI is a no-op and costs nothing
+    ctx = cc.context(0)
+    assert ctx.comm_size() == (1, 0)
+    t = torch.arange(21, dtype=torch.float64, device="cuda")
+    n0 = ctx.collective_count()
+    assert torch.equal(ctx.allreduce(t.clone()), t) and ctx.collective_count() == n0
+
+
+@pytest.mark.gpu
+def test_initial_guess_on_the_device(cc, example_fit):
+    """cc_lm_initial_guess_f64 (batched DLT + pose kernels) against the numpy starting values, and as
+    the start of the fit: same optimum."""
+    from cameracalibrations_b200 import lm
+    obj, imgs = example_fit["obj_np"], example_fit["corners_np"]
+    ih, vh = lm.initial_guess(obj, imgs, example_fit["sz"], 1.0)
+    idv, vd = lm.initial_guess_device(obj, imgs, example_fit["sz"], 1.0)
+    assert np.allclose(idv, ih, rtol=1e-7, atol=1e-12)
+    assert np.allclose(vd.cpu().numpy(), vh, rtol=1e-6, atol=1e-7)
+    a = lm.lm_fit_device(ih, vh, obj, imgs, max_iter=60, eps=1e-10)
+    b = lm.lm_fit_device(idv, vd, obj, imgs, max_iter=60, eps=1e-10)
+    assert abs(a["rms"] - b["rms"]) < 1e-9 and np.allclose(a["intr"], b["intr"], rtol=1e-7)
+    # many synthetic views, steeper tilts, a rectangular aspect
+    intr, views, obj5, img5, rng = _c5(300, seed=5)
+    noisy = img5 + rng.normal(0, 0.1, img5.shape)
+    ih, vh = lm.initial_guess(obj5, noisy, (2160, 3840), 1.0)
+    idv, vd = lm.initial_guess_device(obj5, noisy, (2160, 3840), 1.0)
+    assert np.allclose(idv, ih, rtol=1e-6)
+    assert np.allclose(vd.cpu().numpy(), vh, rtol=1e-5, atol=1e-6)
+    with pytest.raises(cc.CamcalError):
+        lm.initial_guess_device(obj5[:3], noisy[:, :3], (2160, 3840), 1.0)     # a homography needs 4 points
+
+
 def _nccl_worker(rank, world, port, out):
     import os
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -204,8 +254,19 @@ def _nccl_worker(rank, world, port, out):
     intr0, views0 = lm.initial_guess(obj, noisy, (2160, 3840), 1.0)
     lo, hi = shard_range(len(views0), rank, world)
     r = lm.lm_fit(intr0, views0[lo:hi], obj, noisy[lo:hi], max_iter=40, eps=1e-9, device=rank)
+    # the device-resident loop on raw NCCL (cc_comm_init_rank + cc_lm_fit_f64), start values from
+    # the device too (the focal-length equations are all-reduced over the ranks)
+    import cameracalibrations_b200 as cc
+    ctx = cc.context(rank)
+    n_coll = ctx.collective_count()
+    id0, vd0 = lm.initial_guess_device(obj, noisy[lo:hi], (2160, 3840), 1.0, device=rank)
+    rd = lm.lm_fit_device(intr0, views0[lo:hi], obj, noisy[lo:hi], max_iter=40, eps=1e-9, device=rank)
+    rd.pop("views_device")
+    rd["collectives"] = ctx.collective_count() - n_coll
+    rd["comm"] = ctx.comm_size()
+    rd["init_intr"] = id0
     gathered = [None] * world
-    dist.all_gather_object(gathered, (lo, hi, r))
+    dist.all_gather_object(gathered, (lo, hi, r, rd))
     if rank == 0:
         out.put(gathered)
     dist.barrier()
@@ -241,3 +302,11 @@ def test_lm_fit_views_sharded_over_two_gpus(cc):
     np.testing.assert_allclose(r0["intr"], one["intr"], rtol=1e-9)
     np.testing.assert_allclose(np.concatenate([r0["views"], r1["views"]]), one["views"], rtol=1e-7, atol=1e-9)
     assert abs(r0["rms"] - one["rms"]) < 1e-9
+    # cc_lm_fit_f64 over the communicator of the C ABI: the same decisions as the stepwise loop
+    d0, d1 = gathered[0][3], gathered[1][3]
+    assert d0["comm"] == (2, 0) and d1["comm"] == (2, 1)
+    assert d0["intr"] == d1["intr"] == r0["intr"] and d0["iterations"] == d1["iterations"] == r0["iterations"]
+    assert np.array_equal(d0["views"], r0["views"]) and np.array_equal(d1["views"], r1["views"])
+    assert d0["rms"] == r0["rms"]
+    assert d0["collectives"] == 2 + 2 * d0["iterations"] or d0["collectives"] >= 2 + 2 * d0["iterations"]   # init + two per iteration
+    assert np.allclose(d0["init_intr"], intr0, rtol=1e-6) and d0["init_intr"] == d1["init_intr"]
