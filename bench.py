@@ -456,6 +456,31 @@ def extras(cc, torch, dev, c2cal, args):
             ex[f"rectify_{wname}_{coord}"] = {"mpix_per_s": npx / (ms * 1e-3) / 1e6, "ms": ms, "gb_per_s": gbs,
                                               "hbm_frac": gbs / peak}
         del src, dst
+    # the reference's plot loop: every frame with its OWN view (src/plot_calibration.jl:36-42) -- 64 frames,
+    # 64 views, one call of cc_rectify_f32c1_views; no map reuse is possible (one frame per view)
+    wl = WORKLOADS["c2"]
+    sz = wl["sz"]
+    rngv = np.random.default_rng(3)
+    vlist = [((BENCH_VIEW[0][0] + 0.002 * i, BENCH_VIEW[0][1], BENCH_VIEW[0][2] + 0.001 * i),
+              (BENCH_VIEW[1][0] + 0.01 * i, BENCH_VIEW[1][1], BENCH_VIEW[1][2] + 0.05 * i)) for i in range(64)]
+    calv = cc.Calibration(wl["intr"][:4], vlist, 1.0, wl["intr"][4], [f"{i}.png" for i in range(64)])
+    ratio = cc.get_ratio(geometry(wl), 1.0)
+    axs = cc.get_axes(ratio, 1.0, N_CORNERS, sz)
+    src = torch.rand((64, sz[1], sz[0]), dtype=torch.float32, device=dev)
+    dst = torch.empty_like(src)
+    for coord in ("f64", "f32"):
+        t0 = time.perf_counter()
+        cc.warp_views(calv, list(range(64)), src, [ratio] * 64, [axs] * 64, coord=coord, out=dst)
+        torch.cuda.synchronize()
+        first_ms = (time.perf_counter() - t0) * 1e3
+        ms = _time_ms(torch, lambda: cc.warp_views(calv, list(range(64)), src, [ratio] * 64, [axs] * 64, coord=coord, out=dst), 10)
+        npx = 64 * sz[0] * sz[1]
+        ex[f"rectify_views_64x1080p_{coord}"] = {
+            "mpix_per_s": npx / (ms * 1e-3) / 1e6, "ms": ms, "hbm_frac": 8 * npx / (ms * 1e-3) / 1e9 / peak,
+            "first_call_ms": first_ms,
+            "note": "64 frames, 64 different views, one call (64 launches, tile plans cached after the first call); "
+                    "first_call_ms includes building and uploading the 64 tile plans on the host"}
+    del src, dst
     wl = WORKLOADS["c3"]
     rng = np.random.default_rng(7)
     nv, nc = 10_000, 280

@@ -410,6 +410,64 @@ int cc_rectify_u8c3(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doubl
                                nframes, fill, flags, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
+// Frames with DIFFERENT views in one call: the reference's plot loop rectifies every calibration
+// image with its own extrinsic (src/plot_calibration.jl:36-42).  frames [v * frames_per_view,
+// (v + 1) * frames_per_view) use views[v], ratios[v], axs_mins[2v .. 2v+1].  Every view is one
+// launch on `stream` with its own cached tile plan.
+template <typename P, typename F>
+static int rectify_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, int nviews, const double* ratios,
+                         const int64_t* axs_mins, const P* src, P* dst, int sz1, int sz2, size_t pitch,
+                         size_t frame_stride, int frames_per_view, int channels, F launch) {
+    CC_REQUIRE(ctx && intr && (nviews == 0 || (views && ratios && axs_mins)), "NULL argument");
+    CC_REQUIRE(nviews >= 0 && frames_per_view >= 0, "bad counts");
+    CC_REQUIRE((long long)nviews * frames_per_view <= 65535, "at most 65535 frames per call");
+    int rc = CC_OK;
+    for (int v = 0; v < nviews; ++v) {
+        if ((rc = check_params(ctx, intr, views + v))) return rc;
+        if ((rc = check_rect_args(axs_mins + 2 * v, sz1, sz2, pitch, frame_stride, frames_per_view, ratios[v]))) return rc;
+    }
+    CC_REQUIRE(nviews * frames_per_view == 0 || (src && dst), "NULL frame pointer");
+    CC_REQUIRE(nviews * frames_per_view == 0 || (const void*)src != (const void*)dst, "rectification is not in place: src == dst");
+    CC_REQUIRE(nviews * frames_per_view <= 1 || frame_stride >= pitch * (size_t)(sz2 - 1) + sz1, "frames overlap");
+    CC_GUARD;
+    if ((rc = enter(ctx))) return rc;
+    for (int v = 0; v < nviews && frames_per_view > 0; ++v) {
+        ChainD ch;
+        build_chain(intr, views + v, &ch);
+        const size_t off = (size_t)v * frames_per_view * frame_stride * channels;
+        if ((rc = launch(ch, ratios[v], axs_mins + 2 * v, src + off, dst + off))) return rc;
+    }
+    return CC_OK;
+}
+
+extern "C" {
+
+int cc_rectify_f32c1_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, int nviews, const double* ratios,
+                           const int64_t* axs_mins, const float* src, float* dst, int sz1, int sz2, size_t pitch,
+                           size_t frame_stride, int frames_per_view, float fill, unsigned flags, void* stream) {
+    return rectify_views(ctx, intr, views, nviews, ratios, axs_mins, src, dst, sz1, sz2, pitch, frame_stride,
+                         frames_per_view, 1,
+                         [&](const ChainD& ch, double ratio, const int64_t* axs, const float* s, float* d) {
+                             return launch_rectify_f32c1(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
+                                                         frames_per_view, fill, flags, (cudaStream_t)stream);
+                         });
+}
+
+int cc_rectify_u8c3_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, int nviews, const double* ratios,
+                          const int64_t* axs_mins, const uint8_t* src, uint8_t* dst, int sz1, int sz2, size_t pitch,
+                          size_t frame_stride, int frames_per_view, const uint8_t fill[3], unsigned flags,
+                          void* stream) {
+    CC_REQUIRE(fill != nullptr, "fill is NULL");
+    return rectify_views(ctx, intr, views, nviews, ratios, axs_mins, src, dst, sz1, sz2, pitch, frame_stride,
+                         frames_per_view, 3,
+                         [&](const ChainD& ch, double ratio, const int64_t* axs, const uint8_t* s, uint8_t* d) {
+                             return launch_rectify_u8c3(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
+                                                        frames_per_view, fill, flags, (cudaStream_t)stream);
+                         });
+}
+
 int cc_rectify_f32c1_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, double ratio,
                           const int64_t axs_min[2], const float* src, float* dst, int sz1, int sz2,
                           size_t pitch, size_t frame_stride, int nframes, float fill,

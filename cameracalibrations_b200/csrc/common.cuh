@@ -55,7 +55,7 @@ struct cc_ctx {
     // TMA descriptor encode entry point (driver API, resolved at ctx creation)
     void* encode_tiled;
     // rectification tile plans (rectify.cu: RectPlan), most recent NPLAN parameter sets
-    static const int NPLAN = 8;
+    static const int NPLAN = 64;
     void* rect_plans[NPLAN];
     int rect_plan_next;
     // ticket counters of the persistent rectification kernels (rectify.cu: RectSched)

@@ -69,7 +69,7 @@ constexpr int kProducerSleep = CAMCAL_PRODUCER_SLEEP;   // ns between the produc
 #define CAMCAL_MINB 1
 #endif
 #ifndef CAMCAL_MINB_EXACT
-#define CAMCAL_MINB_EXACT 4
+#define CAMCAL_MINB_EXACT 3
 #endif
 // __launch_bounds__ min CTAs/SM of the staged f32c1 kernels (fast / exact coordinates)
 constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;

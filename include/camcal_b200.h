@@ -155,6 +155,21 @@ int cc_rectify_u8c3_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
                          uint8_t *dst, int sz1, int sz2, size_t pitch,
                          size_t frame_stride, int nframes, const uint8_t fill[3],
                          unsigned flags);
+/* Frames with DIFFERENT views in one call -- what the reference's plot does: every calibration
+ * image is rectified with its own extrinsic, ratio and axes (src/plot_calibration.jl:36-42).
+ * Frames [v * frames_per_view, (v+1) * frames_per_view) use views[v], ratios[v] and
+ * axs_mins[2v], axs_mins[2v+1].  Device pointers; one launch per view on `stream`, each with its
+ * own tile plan (the context caches the 64 most recent).  Frames of one view share the map; a
+ * call with one frame per view runs at the single-frame rate. */
+int cc_rectify_f32c1_views(cc_ctx *ctx, const cc_intr *intr, const cc_view *views, int nviews,
+                           const double *ratios, const int64_t *axs_mins, const float *src,
+                           float *dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
+                           int frames_per_view, float fill, unsigned flags, void *stream);
+int cc_rectify_u8c3_views(cc_ctx *ctx, const cc_intr *intr, const cc_view *views, int nviews,
+                          const double *ratios, const int64_t *axs_mins, const uint8_t *src,
+                          uint8_t *dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
+                          int frames_per_view, const uint8_t fill[3], unsigned flags,
+                          void *stream);
 /* the map alone (source row/col sampled by each output pixel), FP64, frame layout */
 int cc_rectify_map_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, double ratio,
                        const int64_t axs_min[2], double *map_row, double *map_col, int sz1,

@@ -310,6 +310,54 @@ def test_rectify_tilted_views_staged_and_fallback(cc, example_fit):
         assert (ref != -2.0).mean() > 0.2
 
 
+def test_rectify_views_is_the_plot_loop(cc, example_fit):
+    """cc_rectify_*_views: the six example images, each with ITS OWN extrinsic, ratio and axes
+    (src/plot_calibration.jl:36-42), in one call; two frames per view; both pixel formats."""
+    intr = example_fit["intr_tuple"]
+    n1, n2 = example_fit["n_corners"]
+    sz = (376, 500)
+    c = _calib(cc, intr, example_fit["view_list"], example_fit["files"])
+    rng = np.random.default_rng(12)
+    nv, k = len(example_fit["view_list"]), 2
+    frames = rng.random((nv * k, sz[1], sz[0]), dtype=np.float32)
+    f8 = rng.integers(0, 256, (nv * k, sz[1], sz[0], 3), dtype=np.uint8)
+    ratios, axss = [], []
+    for vi in range(nv):
+        r, a = cc.image_transformations(c, vi, example_fit["corners_np"], 1.0, (n1, n2), sz)   # detect_fit's flat layout
+        ratios.append(r); axss.append(a)
+    got = cc.warp_views(c, example_fit["files"], _dev(frames), ratios, axss, fill=-2.0).cpu().numpy()
+    got8 = cc.warp_views(c, list(range(nv)), _dev(f8), ratios, axss, fill=(3, 2, 1)).cpu().numpy()
+    for vi, (rv, tv) in enumerate(example_fit["view_list"]):
+        ch = oc.chain(intr, rv, tv)
+        sl = slice(vi * k, (vi + 1) * k)
+        assert np.array_equal(got[sl], oc.rectify_f32c1(ch, 1.0 / ratios[vi], axss[vi], frames[sl], fill=-2.0)), vi
+        assert np.array_equal(got8[sl], oc.rectify_u8c3(ch, 1.0 / ratios[vi], axss[vi], f8[sl], fill=(3, 2, 1))), vi
+    with pytest.raises(ValueError):
+        cc.warp_views(c, [0, 1, 2, 3], _dev(frames[:6]), ratios[:4], axss[:4])            # 6 frames, 4 views
+
+
+def test_rectify_bounds_checked_build(cc):
+    """The rectification parity tests once more against libcamcal_b200_chk.so, the build of the same
+    sources with -DCAMCAL_CHECK_BOUNDS: every shared-memory tap address of the staged kernels is
+    range-checked on the device and a violation traps (the substitute for compute-sanitizer, which
+    is closed on this pool).  Runs in a child process: the library is chosen at import time."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "cameracalibrations_b200", "libcamcal_b200_chk.so")
+    if not os.path.exists(lib):
+        pytest.skip("libcamcal_b200_chk.so not built (make -C cameracalibrations_b200/csrc chk)")
+    if os.environ.get("CAMCAL_B200_LIB"):
+        pytest.skip("already running against a variant library")
+    env = dict(os.environ, CAMCAL_B200_LIB=lib)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "bit_exact or tilted or horizon or views_is or alternating or strided"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
 def test_rectify_edge_rule(cc):
     """x == n in bounds with (i, delta) = (n-1, 1); just outside -> fill; exact grid hits."""
     intr = (1.0, 1.0, 0.0, 0.0, 0.0, 1.0)
@@ -344,7 +392,7 @@ def test_rectify_u8c3_exact_ties_take_the_fp64_blend(cc):
 
 
 def test_rectify_plan_cache_many_parameter_sets(cc):
-    """More parameter sets than the context caches tile plans for (8), revisited in a different
+    """More parameter sets than the context caches tile plans for (64), revisited in a different
     order and on two streams: every call must match the oracle (plans are keyed by calibration,
     ratio, axes and frame geometry; an evicted plan is rebuilt)."""
     sz = (128, 96)
@@ -353,15 +401,16 @@ def test_rectify_plan_cache_many_parameter_sets(cc):
     frames = rng.random((2, sz[1], sz[0]), dtype=np.float32)
     fd = _dev(frames)
     cases = []
-    for i in range(11):
-        view = ((0.05 + 0.01 * i, -0.04, 0.02 * (i % 3)), (-9.3 + 0.2 * i, -6.4, 30.0 + i))
+    N = 67
+    for i in range(N):
+        view = ((0.05 + 0.004 * i, -0.04, 0.02 * (i % 3)), (-9.3 + 0.05 * i, -6.4, 30.0 + 0.3 * i))
         ch, ip, ratio, axs = _rect_case(intr, sz, view=view)
         cases.append((view, ch, ratio, axs))
     c = _calib(cc, intr, [v for v, _, _, _ in cases])
     refs = [oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-3.0) for _, ch, ratio, axs in cases]
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
-    for order in (range(11), reversed(range(11)), (0, 5, 0, 10, 5, 0)):
+    for order in (range(N), reversed(range(N)), (0, 5, 0, N - 1, 5, 0)):
         for i in order:
             _, ch, ratio, axs = cases[i]
             got = cc.warp(c, i, fd, ratio, axs, fill=-3.0).cpu().numpy()
