@@ -311,16 +311,18 @@ def warp_views(c: Calibration, extrinsics, frames, ratios, axs_mins, fill=None, 
     return out
 
 
-def rectify_map(c: Calibration, extrinsic, ratio: float, axs_min, sz, device=None):
-    """Source (row, col) sampled by every output pixel, FP64, as two (sz2, sz1) CUDA tensors."""
+def rectify_map(c: Calibration, extrinsic, ratio: float, axs_min, sz, device=None, coord: str = "f64"):
+    """Source (row, col) sampled by every output pixel as two (sz2, sz1) CUDA tensors: FP64 (the
+    reference's map) or, coord="f32", the FP32 map of the fast path."""
     vi = c._index(extrinsic)
     dev = _default_device() if device is None else int(device)
     ctx = _lib.context(dev)
     sz1, sz2 = int(sz[0]), int(sz[1])
-    mr = torch.empty((sz2, sz1), dtype=torch.float64, device=f"cuda:{dev}")
+    mr = torch.empty((sz2, sz1), dtype=torch.float64 if coord == "f64" else torch.float32, device=f"cuda:{dev}")
     mc = torch.empty_like(mr)
     axs = (C.c_int64 * 2)(int(axs_min[0]), int(axs_min[1]))
-    check(lib.cc_rectify_map_f64(ctx.handle, C.byref(c._intr), C.byref(c._views[vi]), float(ratio), axs,
+    fn = lib.cc_rectify_map_f64 if coord == "f64" else lib.cc_rectify_map_f32
+    check(fn(ctx.handle, C.byref(c._intr), C.byref(c._views[vi]), float(ratio), axs,
                                  _t_ptr(mr), _t_ptr(mc), sz1, sz2, C.c_size_t(sz1), _stream_ptr(dev)))
     return mr, mc
 

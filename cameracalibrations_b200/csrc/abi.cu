@@ -41,6 +41,8 @@ int launch_rectify_u8c3(cc_ctx*, const ChainD&, double, const int64_t[2], const 
                         int, int, size_t, size_t, int, const uint8_t[3], unsigned, cudaStream_t);
 int launch_rectify_map(cc_ctx*, const ChainD&, double, const int64_t[2], double*, double*, int, int,
                        size_t, cudaStream_t);
+int launch_rectify_map_f32(cc_ctx*, const ChainD&, double, const int64_t[2], float*, float*, int, int,
+                           size_t, cudaStream_t);
 int launch_reproj_jtj(cc_ctx*, const cc_intr*, double, const cc_view*, int, const double*,
                       const double*, int, double*, double*, cudaStream_t);
 int launch_calc_errors(cc_ctx*, const cc_intr*, const cc_view*, int, const double*, const double*,
@@ -520,6 +522,21 @@ int cc_rectify_map_f64(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, do
     build_chain(intr, view, &ch);
     return launch_rectify_map(ctx, ch, ratio, axs_min, map_row, map_col, sz1, sz2, pitch,
                               (cudaStream_t)stream);
+}
+
+int cc_rectify_map_f32(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, double ratio,
+                       const int64_t axs_min[2], float* map_row, float* map_col, int sz1, int sz2,
+                       size_t pitch, void* stream) {
+    int rc = check_params(ctx, intr, view);
+    if (rc) return rc;
+    if ((rc = check_rect_args(axs_min, sz1, sz2, pitch, pitch * (size_t)sz2, 1, ratio))) return rc;
+    CC_REQUIRE(map_row && map_col, "NULL map pointer");
+    CC_GUARD;
+    if ((rc = enter(ctx))) return rc;
+    ChainD ch;
+    build_chain(intr, view, &ch);
+    return launch_rectify_map_f32(ctx, ch, ratio, axs_min, map_row, map_col, sz1, sz2, pitch,
+                                  (cudaStream_t)stream);
 }
 
 // get_ratio, src/plot_calibration.jl:8-13

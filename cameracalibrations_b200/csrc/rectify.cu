@@ -145,6 +145,27 @@ rectify_map_kernel(const RectExact p, const RectGeom g, double* __restrict__ map
     }
 }
 
+// the FP32 fast path's map: the same arithmetic as the fast staged kernels (rect_row_term /
+// rect_coord on RectFast), written out as floats
+__global__ void __launch_bounds__(kConsumerThreads)
+rectify_map_f32_kernel(const RectFast p, const RectGeom g, float* __restrict__ map_row,
+                       float* __restrict__ map_col) {
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = blockIdx.x * kT + lane_id;
+    if (a >= g.sz1) return;
+    const RowTermF rt = rect_row_term(p, g.axs0 + a);
+#pragma unroll
+    for (int e = 0; e < kT / kWarps; ++e) {
+        const int b = blockIdx.y * kT + warp * (kT / kWarps) + e;
+        if (b < g.sz2) {
+            float row, col;
+            rect_coord(p, rt, (float)(g.axs1 + b) - p.c2, row, col);
+            map_row[(long long)b * g.pitch + a] = row;
+            map_col[(long long)b * g.pitch + a] = col;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------
@@ -645,6 +666,16 @@ int launch_rectify_map(cc_ctx* ctx, const ChainD& chd, double ratio, const int64
     const RectGeom g = make_geom(axs_min, sz1, sz2, pitch, pitch * (size_t)sz2, 1);
     const dim3 grid((sz1 + kT - 1) / kT, (sz2 + kT - 1) / kT);
     rectify_map_kernel<<<grid, kConsumerThreads, 0, st>>>(make_exact(chd, ratio), g, map_row, map_col);
+    ctx->launches++;
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_rectify_map_f32(cc_ctx* ctx, const ChainD& chd, double ratio, const int64_t axs_min[2],
+                           float* map_row, float* map_col, int sz1, int sz2, size_t pitch, cudaStream_t st) {
+    const RectGeom g = make_geom(axs_min, sz1, sz2, pitch, pitch * (size_t)sz2, 1);
+    const dim3 grid((sz1 + kT - 1) / kT, (sz2 + kT - 1) / kT);
+    rectify_map_f32_kernel<<<grid, kConsumerThreads, 0, st>>>(make_fast(chd, ratio, g), g, map_row, map_col);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
     return CC_OK;

@@ -175,6 +175,12 @@ int cc_rectify_map_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, do
                        const int64_t axs_min[2], double *map_row, double *map_col, int sz1,
                        int sz2, size_t pitch, void *stream);
 
+/* the map the CC_COORD_F32 fast path samples (same arithmetic as its kernels), FP32: stated to lie
+ * within 1e-3 px of the FP64 map wherever that is inside the frame */
+int cc_rectify_map_f32(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, double ratio,
+                       const int64_t axs_min[2], float *map_row, float *map_col, int sz1,
+                       int sz2, size_t pitch, void *stream);
+
 /* get_ratio / get_axes (src/plot_calibration.jl:1-13): tiny host-side helpers so a
  * binding needs nothing else to drive cc_rectify_*.  corners: (a, b) at [a + n1*b]. */
 int cc_get_ratio(const double *rows, const double *cols, int n1, int n2,
