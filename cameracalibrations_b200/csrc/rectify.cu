@@ -37,10 +37,10 @@ constexpr int kWarps = 4;              // consumer warps per CTA
 #define CAMCAL_TL_F32 32
 #endif
 constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTLf / kWarps of them)
-constexpr int kTLmax = 64;
+constexpr int kTLmax = 32;             // most lines of a tile (sizes the per-stage q2 slots)
 // most frames one unit rectifies with one map (measured, profiles/r1_rectify.md: the costlier the
 // map, the larger the group; the cheaper, the finer the units for the tail of the ticket queue)
-constexpr int kFGf32Exact = 12, kFGf32Fast = 4, kFGu8Exact = 16, kFGu8Fast = 8;
+constexpr int kFGf32Exact = 12, kFGf32Fast = 4, kFGu8Exact = 16, kFGu8Fast = 12;
 #ifndef CAMCAL_TL_U8
 #define CAMCAL_TL_U8 32
 #endif
@@ -53,10 +53,17 @@ constexpr int kTLu = CAMCAL_TL_U8;     // u8c3: lines per tile
 #define CAMCAL_FLOOR2 1
 #endif
 constexpr int kFloorMode1 = CAMCAL_FLOOR1, kFloorMode2 = CAMCAL_FLOOR2;
-constexpr int kMaxStages = 4;
+#ifndef CAMCAL_MAX_STAGES
+#define CAMCAL_MAX_STAGES 8
+#endif
+constexpr int kMaxStages = CAMCAL_MAX_STAGES;
+// dynamic shared memory one CTA may spend on its ring (4 resident CTAs of 48 KB + static slots fit in 227 KB)
+#ifndef CAMCAL_RING_BYTES
+#define CAMCAL_RING_BYTES (48 * 1024)
+#endif
 // staged line pitch granularity in bytes, per pixel format (16: dense boxes; 128: all 32 banks, see plan_boxes)
 #ifndef CAMCAL_PITCH_ALIGN_U8
-#define CAMCAL_PITCH_ALIGN_U8 128
+#define CAMCAL_PITCH_ALIGN_U8 0        // 0: the bank-disjoint pitch of plan_boxes; else round the line up to this many bytes
 #endif
 #ifndef CAMCAL_PITCH_ALIGN_F32
 #define CAMCAL_PITCH_ALIGN_F32 16
@@ -84,7 +91,7 @@ constexpr int kConsumerThreads = 32 * kWarps;
 
 struct TileCfg {
     int box1, box2;        // staged box, in pixels (box1 along the contiguous axis)
-    int pitch_b;           // bytes between consecutive lines of a staged box (multiple of 128, see plan_boxes)
+    int pitch_b;           // bytes between consecutive lines of a staged box (see plan_boxes)
     int stages;
     int ntiles2;           // tiles along the second axis
     int box_bytes;         // bytes one TMA load delivers = stage stride (multiple of 128)
@@ -99,7 +106,7 @@ struct __align__(16) TileHdr {
     double Mk1, Mk2;       // exact: 2^52 - K   (K = global 1-based index of local tap 0)
     float mk1, mk2;        // fast:  1.5*2^23 - K
     uint32_t R1, R2;       // number of valid local first-tap indices per axis (0: nothing staged)
-    int x0, y0;            // box origin (0-based texel indices; may be negative)
+    int x0, y0;            // box origin: TMA coordinates (x0: f32 texels / u8 BYTES of the line, multiple of 16 bytes; y0: lines; may be negative)
     uint32_t base_off;     // byte offset of local tap (0, 0) inside the stage (pixels are 4 or 3 bytes)
     uint32_t pad;
 };
@@ -248,6 +255,7 @@ struct RectPlan {
     int need1, need2;              // largest footprint (pixels), incl. taps and slack
     int box1, box2, box_bytes;     // staged box (pixels) and its size; box_bytes == 0: not stageable
     int pitch_b;                   // bytes per staged line
+    int tilt;                      // sign of d(source line)/d(first output index): which way a warp's taps change lines
     std::vector<int> origin;       // per tile: floor(min row), floor(min col) of the perimeter samples
     std::vector<unsigned char> p3_ok;
     std::vector<TileHdr> hdr;      // tile headers
@@ -282,12 +290,14 @@ static void plan_footprints(RectPlan* p) {
     p->origin.assign((size_t)p->n1 * p->n2 * 2, -4);
     p->p3_ok.assign((size_t)p->n1 * p->n2, 1);
     int m1 = 0, m2 = 0;
+    long long tilt = 0;
     for (int t1 = 0; t1 < p->n1; ++t1) {
         const int a_lo = t1 * tw, a_hi = std::min(a_lo + tw - 1, g.sz1 - 1);
         for (int t2 = 0; t2 < p->n2; ++t2) {
             const int b_lo = t2 * tl, b_hi = std::min(b_lo + tl - 1, g.sz2 - 1);
             double rmin = 0, rmax = 0, cmin = 0, cmax = 0;
             bool finite = true;
+            double c_first = 0, c_last = 0;         // source line at the two ends of the tile's first output line
             for (int j = 0; j < 32; ++j) {          // 8 samples on each of the four edges
                 const int k = j & 7;
                 const bool far = (j & 8) != 0;
@@ -298,6 +308,8 @@ static void plan_footprints(RectPlan* p) {
                 host_coord(ch, inv_ratio, g.axs0 + ca, g.axs1 + cb, &r, &c);
                 finite = finite && std::isfinite(r) && std::isfinite(c);
                 if (j == 0) { rmin = rmax = r; cmin = cmax = c; }
+                if (j == 16) c_first = c;
+                if (j == 23) c_last = c;
                 rmin = std::min(rmin, r); rmax = std::max(rmax, r);
                 cmin = std::min(cmin, c); cmax = std::max(cmax, c);
             }
@@ -316,6 +328,7 @@ static void plan_footprints(RectPlan* p) {
             const size_t t = (size_t)t1 * p->n2 + t2;
             p->p3_ok[t] = p3_ok ? 1 : 0;
             if (!finite) continue;                  // origin stays at (-4, -4): the range tests fail
+            tilt += (c_last > c_first) - (c_last < c_first);
             // clamp so that far-away footprints still give a legal (fully out-of-frame) box
             const double rc = std::min(std::max(rmin, -4.0), (double)g.sz1 + 4.0);
             const double cc_ = std::min(std::max(cmin, -4.0), (double)g.sz2 + 4.0);
@@ -330,28 +343,47 @@ static void plan_footprints(RectPlan* p) {
     // taps floor-1 .. floor; 2 texels of slack below (origin) and 1 above
     p->need1 = m1 + 2 + 3;
     p->need2 = m2 + 2 + 3;
+    p->tilt = tilt >= 0 ? 1 : -1;
 }
 
 // box size from the footprint; tile headers
+//
+// f32c1 (4-byte pixels): the box origin along the first axis is a texel index rounded down to 4
+// texels (16 bytes, what TMA can address); dense lines (pitch = box width).
+//
+// u8c3 (3-byte pixels): the TMA tensor is the line of BYTES, so the origin is a byte offset rounded
+// down to 16 bytes -- at most 15 bytes (5 texels) of slack instead of the 15 texels a texel-granular
+// origin needs -- and the tile header carries the byte offset of local tap 0.  Line pitch: the lanes
+// of a warp read consecutive 3-byte texels (32 lanes span ~24-26 words); on a rotated map the upper
+// part of the warp samples the neighbouring source line, `pitch` bytes away.  Both parts hit disjoint
+// banks iff the pitch in words is +4 (mod 32) in the direction the source line changes: with a
+// multiple of 128 bytes the two lanes at the change share a bank (ncu, round 2: 1.2 wavefronts per
+// LDS), with anything else whole groups of lanes collide (1.7 wavefronts with 192-byte lines).
+static int floor_to(int v, int m) { return v >= 0 ? (v / m) * m : -(((-v) + m - 1) / m) * m; }
+
 static void plan_boxes(RectPlan* p) {
     const RectGeom& g = p->key.g;
     const int pxb = p->key.pxb;
-    // box1 in pixels with a byte length that is a multiple of 16; the stage size must be a
-    // multiple of 128 bytes so every stage base stays 128-byte aligned
-    const int unit = (pxb == 4) ? 4 : 16;
-    // (+ unit - 1: the box origin is rounded down to a multiple of `unit` pixels)
-    p->box1 = (p->need1 + unit - 1 + unit - 1) / unit * unit;
-    // Line pitch of the staged u8 box: a multiple of 128 bytes (all 32 banks).  The lanes of a warp read
-    // consecutive texels, but on a rotated map part of the warp samples source line i2 and the rest
-    // line i2+1; with any other pitch the second group lands on banks the first one uses (ncu, round 2:
-    // 1.7 wavefronts per LDS with 192-byte lines, which made the byte loads of the u8 kernel the bound).
-    // The extra columns cost shared memory and L2->SM traffic, not DRAM traffic.  The f32 kernels are
-    // not bound by the shared-memory pipe and measured 3-4 % faster with dense boxes (more stages fit).
-    const int align = (pxb == 4) ? CAMCAL_PITCH_ALIGN_F32 : CAMCAL_PITCH_ALIGN_U8;
-    p->pitch_b = (p->box1 * pxb + align - 1) / align * align;
-    p->box1 = p->pitch_b / pxb;                       // usable pixels per line
+    if (pxb == 4) {
+        const int unit = 4;
+        p->box1 = (p->need1 + unit - 1 + unit - 1) / unit * unit;      // + unit - 1: the origin is rounded down
+        const int align = CAMCAL_PITCH_ALIGN_F32;
+        p->pitch_b = (p->box1 * pxb + align - 1) / align * align;
+        p->box1 = p->pitch_b / pxb;                                    // usable pixels per line
+    } else {
+        const int need_b = p->need1 * 3 + 15;                          // + 15: the byte origin is rounded down
+        int pitch = (need_b + 15) / 16 * 16;
+#if CAMCAL_PITCH_ALIGN_U8 == 0
+        const int want = p->tilt >= 0 ? 4 : 28;                        // pitch in words, mod 32
+        while ((pitch / 4) % 32 != want) pitch += 16;
+#else
+        pitch = (pitch + CAMCAL_PITCH_ALIGN_U8 - 1) / CAMCAL_PITCH_ALIGN_U8 * CAMCAL_PITCH_ALIGN_U8;
+#endif
+        p->pitch_b = pitch;
+        p->box1 = pitch / 3;
+    }
     p->box2 = p->need2;
-    while (((size_t)p->pitch_b * p->box2) % 128) ++p->box2;
+    while (((size_t)p->pitch_b * p->box2) % 128) ++p->box2;           // every stage base stays 128-byte aligned
     const int box1_elems = (pxb == 4) ? p->pitch_b / 4 : p->pitch_b;
     p->box_bytes = p->pitch_b * p->box2;
     if (box1_elems > 256 || p->box2 > 256 || p->box_bytes > 40 * 1024) p->box_bytes = 0;   // not worth staging
@@ -360,21 +392,32 @@ static void plan_boxes(RectPlan* p) {
     for (size_t t = 0; t < p->hdr.size(); ++t) {
         TileHdr& h = p->hdr[t];
         memset(&h, 0, sizeof(h));
-        int x0 = p->origin[2 * t] - 2;
         const int y0 = p->origin[2 * t + 1] - 2;
-        x0 = (x0 >= 0) ? (x0 / unit) * unit : -(((-x0) + unit - 1) / unit) * unit;
-        // valid local range of the first tap: inside the box (both taps) and inside the frame
-        const int lo1 = std::max(0, -x0), hi1 = std::min(p->box1 - 2, g.sz1 - 2 - x0);
+        // first tap g1 (0-based texel index): inside the box (both taps) and inside the frame
+        int g_lo, g_hi;
+        if (pxb == 4) {
+            const int x0 = floor_to(p->origin[2 * t] - 2, 4);
+            h.x0 = x0;
+            g_lo = std::max(0, x0);
+            g_hi = std::min(x0 + p->box1 - 2, g.sz1 - 2);
+            h.base_off = (uint32_t)(g_lo - x0) * 4u;
+        } else {
+            const int xb0 = floor_to((p->origin[2 * t] - 2) * 3, 16);
+            h.x0 = xb0;
+            g_lo = std::max(0, xb0 >= 0 ? (xb0 + 2) / 3 : 0);                       // 3 g1 >= xb0
+            g_hi = std::min((xb0 + p->pitch_b - 6) >= 0 ? (xb0 + p->pitch_b - 6) / 3 : -1, g.sz1 - 2);   // 3 g1 + 6 <= xb0 + pitch
+            h.base_off = (uint32_t)(3 * g_lo - xb0);
+        }
         const int lo2 = std::max(0, -y0), hi2 = std::min(p->box2 - 2, g.sz2 - 2 - y0);
-        h.x0 = x0; h.y0 = y0;
-        h.R1 = p->p3_ok[t] ? (uint32_t)std::max(0, hi1 - lo1 + 1) : 0u;
+        h.y0 = y0;
+        h.R1 = p->p3_ok[t] ? (uint32_t)std::max(0, g_hi - g_lo + 1) : 0u;
         h.R2 = (uint32_t)std::max(0, hi2 - lo2 + 1);
-        const int k1 = 1 + x0 + lo1, k2 = 1 + y0 + lo2;   // global 1-based index of local tap 0
+        const int k1 = 1 + g_lo, k2 = 1 + y0 + lo2;       // global 1-based index of local tap 0
         h.Mk1 = 4503599627370496.0 - (double)k1;
         h.Mk2 = 4503599627370496.0 - (double)k2;
         h.mk1 = 12582912.0f - (float)k1;
         h.mk2 = 12582912.0f - (float)k2;
-        h.base_off = (uint32_t)lo2 * (uint32_t)p->pitch_b + (uint32_t)lo1 * (uint32_t)pxb;
+        h.base_off += (uint32_t)lo2 * (uint32_t)p->pitch_b;
     }
     p->q2.resize((size_t)g.sz2);
     const double inv_ratio = 1.0 / p->key.ratio;
@@ -449,7 +492,9 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
     RectPlan* plan = plan_get(ctx, ch, ratio, g, tw, tl, pxb, st);
     if (!plan || !plan->box_bytes) return false;
     // measured (profiles/r1_rectify.md): occupancy beats ring depth; small boxes afford more stages
-    int stages = std::min(kMaxStages, std::max(2, 32768 / plan->box_bytes));
+    // the ring hides the TMA round trip: per SM, (stages - 1) x resident CTAs x the USEFUL bytes of a box
+    // must cover bandwidth x latency (~30 KB of reads at the HBM roofline, profiles/r2_rectify.md)
+    int stages = std::min(kMaxStages, std::max(2, CAMCAL_RING_BYTES / plan->box_bytes));
     if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
     while (stages > 2 && stages * plan->box_bytes > 56 * 1024) --stages;
 

@@ -95,6 +95,14 @@ rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_c
 //   skip    : the output pixel itself is outside the frame (partial strip / last tile)
 //   neither : generic path (per-pixel checks, direct global taps): x == n exactly, or a
 //             footprint that leaves the box.  Results never depend on the class.
+// 1: keep e1 = 1 - d1, e2 = 1 - d2 with the map (two DADDs fewer per pixel and frame, 163 instead of
+// 177 instructions per 8 pixels) -- measured SLOWER (0.233 vs 0.221 ms on c2): 127 registers instead
+// of 96 drop the kernel from 4 to 3 resident CTAs per SM.  Kept as a knob.
+#ifndef CAMCAL_F32_KEEP_E
+#define CAMCAL_F32_KEEP_E 0
+#endif
+constexpr bool kKeepE = CAMCAL_F32_KEEP_E != 0;
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
@@ -124,6 +132,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     // the map of the current unit
     uint32_t rel[LPW];                                 // tap (0,0) byte offset inside a stage
     [[maybe_unused]] double wd1[LPW], wd2[LPW];        // exact weights
+    [[maybe_unused]] double we1[LPW], we2[LPW];        // kKeepE: 1 - wd1, 1 - wd2 (the oracle's e1, e2) kept instead of two DADDs per pixel and frame
     [[maybe_unused]] float2 wf1[LPW / 2], wf2[LPW / 2];   // fast weights, pairs of lines
     uint32_t m_staged = 0, m_fill = 0, m_skip = 0;
     bool all_staged = false;                           // warp-uniform: every pixel of every lane staged
@@ -162,6 +171,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                     uint32_t t1, t2, h1, h2;
                     floor_index<kFloorMode1>(row, Mk1, t1, h1, wd1[e]);
                     floor_index<kFloorMode2>(col, Mk2, t2, h2, wd2[e]);
+                    if (kKeepE) { we1[e] = 1.0 - wd1[e]; we2[e] = 1.0 - wd2[e]; }
                     const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 4u;
                     if (st) m_staged |= 1u << e;
@@ -205,12 +215,13 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const float* sframe = src + (long long)pos.z * g.frame_stride;
         float* o = dst + (long long)pos.z * g.frame_stride + off0;
         const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+        const uint32_t sbase1 = sbase + box_pitch_b;    // one uniform base per source line: LDS [R + UR + imm], no per-pixel add
         if (all_staged) {
             float a00[LPW], a10[LPW], a01[LPW], a11[LPW];
 #pragma unroll
             for (int e = 0; e < LPW; ++e) {
                 const uint32_t q = sbase + rel[e];
-                const uint32_t q1 = q + box_pitch_b;
+                const uint32_t q1 = sbase1 + rel[e];
 #ifdef CAMCAL_CHECK_BOUNDS      // debug builds (profiles/mkvariant.sh chk "-DCAMCAL_CHECK_BOUNDS"): taps inside the stage
                 if (q < sbase || q1 + 8u > sbase + (uint32_t)cfg.box_bytes || (q & 3u)) __trap();
 #endif
@@ -220,8 +231,15 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             if (EXACT) {
 #pragma unroll
                 for (int e = 0; e < LPW; ++e) {
-                    __stcs(o, (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
-                                            wd1[e], wd2[e]));
+                    if (kKeepE) {
+                        // opaque to the compiler: otherwise it rematerialises 1 - d per frame to save registers
+                        asm volatile("" : "+d"(we1[e]), "+d"(we2[e]));
+                        __stcs(o, (float)bilerp_e((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
+                                                  wd1[e], we1[e], wd2[e], we2[e]));
+                    } else {
+                        __stcs(o, (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
+                                                wd1[e], wd2[e]));
+                    }
                     o += pitch;
                 }
             } else {

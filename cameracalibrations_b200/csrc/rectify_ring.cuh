@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
     return __shfl_sync(0xffffffffu, u, 0);
 }
 
-// PXB: tensor-map elements per pixel along the first axis (1: f32c1, 3: u8c3 bytes).
+// PXB: multiplier from TileHdr.x0 to the tensor-map coordinate (1: f32c1 texels, and u8c3 whose x0 already is a byte offset).
 // A unit is (strip x, tile y, frame group): the producer publishes one slot per FRAME of the
 // group -- pos = (x, y, frame, 1 on the first frame of a unit) -- so the consumers rebuild the
 // tile's map only when pos.w is set and otherwise just gather.

@@ -25,13 +25,21 @@ namespace cc {
 
 struct Taps6 { uint32_t lo, hi; };   // bytes [o, o+4) and [o+4, o+8) of a byte stream
 
+// PRMT with a selector register whose nibbles are all < 8 (sel6): __byte_perm() would first mask
+// the selector with 0x7777 (one LOP3 per pixel and frame in the hot loop)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 template <typename LD>
 __device__ __forceinline__ Taps6 load6(const uint32_t* words, unsigned o, unsigned sel, LD ld) {
     const uint32_t* w = words + (o >> 2);
     const uint32_t w0 = ld(w), w1 = ld(w + 1), w2 = ld(w + 2);
     Taps6 t;
-    t.lo = __byte_perm(w0, w1, sel);
-    t.hi = __byte_perm(w1, w2, sel);
+    t.lo = prmt(w0, w1, sel);
+    t.hi = prmt(w1, w2, sel);
     return t;
 }
 __device__ __forceinline__ unsigned sel6(unsigned o) { return 0x3210u + 0x1111u * (o & 3u); }
@@ -50,8 +58,8 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t addr) {
 __device__ __forceinline__ Taps6 lds6w(uint32_t wa, unsigned sel) {
     const uint32_t w0 = lds_u32(wa), w1 = lds_u32_off<4>(wa), w2 = lds_u32_off<8>(wa);
     Taps6 t;
-    t.lo = __byte_perm(w0, w1, sel);
-    t.hi = __byte_perm(w1, w2, sel);
+    t.lo = prmt(w0, w1, sel);
+    t.hi = prmt(w1, w2, sel);
     return t;
 }
 // byte k of w as a float without a conversion instruction: 0x4B000000 | b  ==  2^23 + b
@@ -278,7 +286,7 @@ __device__ __forceinline__ TapF load_taps(uint32_t A0, uint32_t A1, unsigned sel
     } else if (kU8Load == 4) {
         // as 3, but only tap a11 (three bytes) through LDS.U8; a01 from two aligned words
         const Taps6 r0 = lds6w(A0, sel);
-        const uint32_t r1lo = __byte_perm(lds_u32(A1), lds_u32_off<4>(A1), sel);
+        const uint32_t r1lo = prmt(lds_u32(A1), lds_u32_off<4>(A1), sel);
         t.m[0] = __byte_perm(r0.lo, 0u, 0x4440); t.m[1] = __byte_perm(r0.lo, 0u, 0x4441); t.m[2] = __byte_perm(r0.lo, 0u, 0x4442);
         t.m[3] = __byte_perm(r0.lo, 0u, 0x4443); t.m[4] = __byte_perm(r0.hi, 0u, 0x4440); t.m[5] = __byte_perm(r0.hi, 0u, 0x4441);
         t.m[6] = __byte_perm(r1lo, 0u, 0x4440); t.m[7] = __byte_perm(r1lo, 0u, 0x4441); t.m[8] = __byte_perm(r1lo, 0u, 0x4442);
@@ -375,7 +383,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        producer_loop<EXACT, TL, 3>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
+        producer_loop<EXACT, TL, 1>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 

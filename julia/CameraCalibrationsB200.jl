@@ -11,6 +11,7 @@
 module CameraCalibrationsB200
 
 using CameraCalibrations: Calibration, RowCol, XYZ
+import CameraCalibrations
 using StaticArrays
 
 const libcamcal = get(ENV, "LIBCAMCAL_B200", "libcamcal_b200.so")
@@ -66,6 +67,22 @@ function context()
     end
     ctx
 end
+
+# ---- load hook (src/io.jl:19-26) ------------------------------------------------------------------
+# `CameraCalibrations.load` rebuilds the closure chains of the object; this wrapper also derives, once,
+# the parameter blocks every batch call passes to the library (by value: no device upload is needed,
+# kernel parameters travel in the launch).  What IS device-resident per calibration is the
+# rectification tile plan, cached inside the context keyed by (parameters, ratio, axes, frame size).
+# The JSON file format is untouched.
+struct DeviceCalibration
+    c::Calibration
+    intr::CcIntr
+    views::Vector{CcView}
+end
+DeviceCalibration(c::Calibration) = DeviceCalibration(c, CcIntr(c), [CcView(c, i) for i in eachindex(c.extrinsics)])
+"`load_b200(file)`: `CameraCalibrations.load(file)` plus the cached parameter blocks."
+load_b200(file) = DeviceCalibration(CameraCalibrations.load(file))
+(d::DeviceCalibration)(args...) = d.c(args...)                       # everything the object can do still works
 
 # ---- batch pixel -> world: bulk form of c.(imgpoints, i), src/buildcalibrations.jl:46 --------
 """
@@ -140,6 +157,42 @@ function warp_batch(c::Calibration, i::Int, imgs::Array{UInt8,4}, ratio::Float64
     out
 end
 
+# The reference's plot loop (src/plot_calibration.jl:36-42) in ONE call: frame v of `imgs` is
+# rectified with view v, ratios[v] and axs[v].  Device-resident arrays are what cc_rectify_*_views
+# takes; this host convenience copies in and out around it.
+function warp_views(d::DeviceCalibration, imgs::Array{Float32,3}, ratios::Vector{Float64},
+                    axss::Vector{<:NTuple{2,<:AbstractUnitRange}}; fill::Float32 = NaN32, fast::Bool = false)
+    sz1, sz2, nf = size(imgs)
+    @assert nf == length(d.views) == length(ratios) == length(axss)
+    out = similar(imgs)
+    for v in 1:nf                                    # host arrays: one pipelined call per view
+        axs_min = Int64[first(axss[v][1]), first(axss[v][2])]
+        check(ccall((:cc_rectify_f32c1_host, libcamcal), Cint,
+                    (Ptr{Cvoid}, Ref{CcIntr}, Ref{CcView}, Cdouble, Ptr{Int64}, Ptr{Cfloat}, Ptr{Cfloat},
+                     Cint, Cint, Csize_t, Csize_t, Cint, Cfloat, Cuint),
+                    context().handle, Ref(d.intr), Ref(d.views[v]), ratios[v], axs_min,
+                    pointer(imgs, (v - 1) * sz1 * sz2 + 1), pointer(out, (v - 1) * sz1 * sz2 + 1),
+                    sz1, sz2, sz1, sz1 * sz2, 1, fill, fast ? 1 : 0))
+    end
+    out
+end
+
+# ---- multi-GPU: one Julia process per GPU (Distributed / MPI), NCCL inside the library ------------
+# rank 0:  id = comm_unique_id();  ship the 128 bytes to the other ranks (MPI.Bcast!, a file, ...)
+# all:     comm_init_rank(nranks, rank, id)
+# then cc_reproj_jtj_f64 + allreduce_shared!, or the whole fit with lm_fit_device!, run over the ranks.
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:cc_comm_unique_id, libcamcal), Cint, (Ptr{UInt8},), id))
+    id
+end
+comm_init_rank(nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:cc_comm_init_rank, libcamcal), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), context().handle, nranks, rank, id))
+"in-place sum over the ranks of `count` doubles at DEVICE pointer `buf`"
+allreduce_shared!(buf::Ptr{Cdouble}, count::Integer; stream::Ptr{Cvoid} = C_NULL) =
+    check(ccall((:cc_allreduce_shared, libcamcal), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Csize_t, Ptr{Cvoid}),
+                context().handle, buf, count, stream))
+
 # ---- residual + normal-equation blocks (what calibrateCamera reduces, src/detect_fit.jl:47) ---
 function reproj_jtj(c::Calibration, aspect::Float64, objpoints::Matrix{Float64},   # 3 x ncorners
                     imgpoints::Array{Float64,3})                                    # 2 x ncorners x nviews
@@ -173,6 +226,27 @@ function lm_fit!(intr::Base.RefValue{CcIntr}, views::Vector{CcView}, aspect::Flo
                 nc, max_iter, eps, rms, its))
     (; k = intr[].k, Rs = [collect(v.rvec) for v in views], ts = [collect(v.tvec) for v in views],
        frow = intr[].frow, fcol = intr[].fcol, crow = intr[].crow, ccol = intr[].ccol, rms = rms[], iterations = its[])
+end
+
+# The same fit on DEVICE arrays (e.g. CUDA.jl CuArrays passed as pointers), over this rank's shard of
+# the views when the context has a communicator: cc_lm_initial_guess_f64 + cc_lm_fit_f64.  The loop
+# state lives on the device; an iteration costs two NCCL all-reduces and no host synchronisation.
+function lm_fit_device!(intr::Base.RefValue{CcIntr}, views::Ptr{CcView}, nviews::Integer, obj::Ptr{Cdouble},
+                        img::Ptr{Cdouble}, ncorners::Integer, sz::NTuple{2,Int}, aspect::Float64,
+                        with_distortion::Bool; max_iter::Int = 30, eps::Float64 = 1e-3, init::Bool = true,
+                        stream::Ptr{Cvoid} = C_NULL)
+    if init
+        check(ccall((:cc_lm_initial_guess_f64, libcamcal), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cint, Cint, Cdouble, Ref{CcIntr}, Ptr{CcView}, Ptr{Cvoid}),
+                    context().handle, obj, img, nviews, ncorners, sz[1], sz[2], aspect, intr, views, stream))
+    end
+    rms, its = Ref{Cdouble}(0), Ref{Cint}(0)
+    check(ccall((:cc_lm_fit_f64, libcamcal), Cint,
+                (Ptr{Cvoid}, Ref{CcIntr}, Cdouble, Cuint, Ptr{CcView}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint,
+                 Cdouble, Ref{Cdouble}, Ref{Cint}, Ptr{Cvoid}),
+                context().handle, intr, aspect, with_distortion ? 0x0f : 0x07, views, nviews, obj, img, ncorners,
+                max_iter, eps, rms, its, stream))
+    (; rms = rms[], iterations = its[])
 end
 
 end # module
