@@ -136,14 +136,40 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Sum 64 per-lane partials over the warp with a HALVING butterfly: at the step with partner mask m a
+// lane keeps one half of its values, sends the other half and adds what its partner sent, so the
+// steps move 32 + 16 + 8 + 4 + 2 = 62 doubles instead of 64 x 5 = 320 (the plain xor butterfly of
+// round 1 spent 660 SHFLs per view: a quarter of the kernel, ncu round 2).  Afterwards lane l holds
+// the warp totals of entries 2l and 2l+1 in v[0], v[1].  Fixed order: bit-reproducible.
+template <int N, int MASK>
+__device__ __forceinline__ void halve_step(double (&v)[64], bool up) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const double keep = up ? v[i + N / 2] : v[i];
+        const double send = up ? v[i] : v[i + N / 2];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+}
+__device__ __forceinline__ void warp_sum64(double (&v)[64], int lane_id) {
+    halve_step<64, 16>(v, (lane_id & 16) != 0);
+    halve_step<32, 8>(v, (lane_id & 8) != 0);
+    halve_step<16, 4>(v, (lane_id & 4) != 0);
+    halve_step<8, 2>(v, (lane_id & 2) != 0);
+    halve_step<4, 1>(v, (lane_id & 1) != 0);
+}
+
 // acc layout: [0,21) JtJ_ee upper | [21,45) JtJ_ei | [45,51) Jtr_e | [51,61) JtJ_ii upper |
 //             [61,65) Jtr_i | [65] sse
+// The Jacobian columns of crow / ccol are the constants (1, 0) / (0, 1): their products are written
+// out as additions (or nothing) instead of FMAs with 1.0 / 0.0 -- 108 instead of 132 accumulation
+// instructions per corner, same values (x * 1 and x * 0 + acc are exact).
 __device__ __forceinline__ void
 reproj_jtj_view(const SharedIntr& in, const cc_view* __restrict__ views, int nviews,
                 const double* __restrict__ obj, const double* __restrict__ img, int ncorners,
                 double* __restrict__ per_view, double* __restrict__ scratch) {
-    const int lane_id = threadIdx.x & 31;
-    const int view = blockIdx.x * kResWarps + (threadIdx.x >> 5);
+    __shared__ double red[kResWarps][66];
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int view = blockIdx.x * kResWarps + warp;
     if (view >= nviews) return;
     double r[3], t[3];
 #pragma unroll
@@ -151,15 +177,18 @@ reproj_jtj_view(const SharedIntr& in, const cc_view* __restrict__ views, int nvi
     ViewGeom g;
     view_geom(r, g);
 
-    double acc[66];
+    double acc[64];            // entries 0..63; 64 (Jtr_i[3]) and 65 (sse) separately
+    double acc64 = 0.0, acc65 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 66; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 64; ++i) acc[i] = 0.0;
+    int mine = 0;              // corners of this lane: J'J entries (crow,crow) and (ccol,ccol)
     const double2* im = reinterpret_cast<const double2*>(img) + (size_t)view * ncorners;
     for (int ci = lane_id; ci < ncorners; ci += 32) {
         const double2 ob = im[ci];
         const double X0 = __ldg(obj + 3 * ci), X1 = __ldg(obj + 3 * ci + 1), X2 = __ldg(obj + 3 * ci + 2);
         double res[2], J[2][10];
         corner_jac(g, t, in, X0, X1, X2, ob.x, ob.y, res, J);
+        ++mine;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             int k = 0;
@@ -168,46 +197,54 @@ reproj_jtj_view(const SharedIntr& in, const cc_view* __restrict__ views, int nvi
 #pragma unroll
                 for (int b = a; b < 6; ++b) { acc[k] = fma(J[rr][a], J[rr][b], acc[k]); ++k; }
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[21 + 4 * a + b] = fma(J[rr][a], J[rr][6 + b], acc[21 + 4 * a + b]);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) acc[45 + a] = fma(J[rr][a], res[rr], acc[45 + a]);
-            k = 51;
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = a; b < 4; ++b) { acc[k] = fma(J[rr][6 + a], J[rr][6 + b], acc[k]); ++k; }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) acc[61 + a] = fma(J[rr][6 + a], res[rr], acc[61 + a]);
-            acc[65] = fma(res[rr], res[rr], acc[65]);
+            for (int a = 0; a < 6; ++a) {
+                acc[21 + 4 * a + 0] = fma(J[rr][a], J[rr][6], acc[21 + 4 * a + 0]);
+                acc[21 + 4 * a + 1 + rr] += J[rr][a];                 // column crow (rr = 0) / ccol (rr = 1) is 1
+                acc[21 + 4 * a + 3] = fma(J[rr][a], J[rr][9], acc[21 + 4 * a + 3]);
+                acc[45 + a] = fma(J[rr][a], res[rr], acc[45 + a]);
+            }
+            acc[51] = fma(J[rr][6], J[rr][6], acc[51]);               // (f, f)
+            acc[52 + rr] += J[rr][6];                                 // (f, crow) / (f, ccol)
+            acc[54] = fma(J[rr][6], J[rr][9], acc[54]);               // (f, k)
+            if (rr == 0) acc[57] += J[0][9]; else acc[59] += J[1][9]; // (crow, k) / (ccol, k)
+            acc[60] = fma(J[rr][9], J[rr][9], acc[60]);               // (k, k)
+            acc[61] = fma(J[rr][6], res[rr], acc[61]);
+            if (rr == 0) acc[62] += res[0]; else acc[63] += res[1];
+            acc64 = fma(J[rr][9], res[rr], acc64);
+            acc65 = fma(res[rr], res[rr], acc65);
         }
     }
-#pragma unroll
-    for (int i = 0; i < 66; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane_id == 0) {
-        double* pv = per_view + (size_t)view * CC_PER_VIEW;
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = a; b < 6; ++b) { pv[6 * a + b] = acc[k]; pv[6 * b + a] = acc[k]; ++k; }
-#pragma unroll
-        for (int i = 0; i < 24; ++i) pv[36 + i] = acc[21 + i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) pv[60 + i] = acc[45 + i];
-        k = 51;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = a; b < 4; ++b) {
-                scratch[(size_t)(4 * a + b) * nviews + view] = acc[k];
-                scratch[(size_t)(4 * b + a) * nviews + view] = acc[k];
-                ++k;
-            }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) scratch[(size_t)(16 + i) * nviews + view] = acc[61 + i];
-        scratch[(size_t)20 * nviews + view] = acc[65];
+    acc[55] = acc[58] = (double)mine;                                 // (crow, crow), (ccol, ccol); [56] (crow, ccol) stays 0
+    warp_sum64(acc, lane_id);
+    acc64 = warp_sum(acc64);
+    acc65 = warp_sum(acc65);
+    red[warp][2 * lane_id] = acc[0];
+    red[warp][2 * lane_id + 1] = acc[1];
+    if (lane_id == 0) { red[warp][64] = acc64; red[warp][65] = acc65; }
+    __syncwarp();
+    const double* rd = red[warp];
+    double* pv = per_view + (size_t)view * CC_PER_VIEW;
+    for (int idx = lane_id; idx < CC_PER_VIEW; idx += 32) {
+        int k;
+        if (idx < 36) {
+            const int a0 = idx / 6, b0 = idx - 6 * a0, a = min(a0, b0), b = max(a0, b0);
+            k = 6 * a - (a * (a - 1)) / 2 + (b - a);
+        } else if (idx < 60) {
+            k = 21 + (idx - 36);
+        } else {
+            k = 45 + (idx - 60);
+        }
+        pv[idx] = rd[k];
+    }
+    if (lane_id < 21) {
+        int k;
+        if (lane_id < 16) {
+            const int a0 = lane_id >> 2, b0 = lane_id & 3, a = min(a0, b0), b = max(a0, b0);
+            k = 51 + 4 * a - (a * (a - 1)) / 2 + (b - a);
+        } else {
+            k = 61 + (lane_id - 16);
+        }
+        scratch[(size_t)lane_id * nviews + view] = rd[k];
     }
 }
 
