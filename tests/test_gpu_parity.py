@@ -292,6 +292,35 @@ def test_rectify_u8c3_bit_exact(cc, sz):
     assert np.array_equal(got_h, ref)
 
 
+@pytest.mark.parametrize("rz", [0.3, -0.3, 0.04, -0.04, 0.9, -0.7])
+@pytest.mark.parametrize("ratio_scale", [1.0, 0.8, 1.25])
+def test_rectify_u8c3_staged_rotations_and_scales(cc, rz, ratio_scale):
+    """The u8 box origin is a BYTE offset (multiple of 16) and the staged line pitch depends on which way the
+    source line changes along a warp (RectPlan.tilt): both rotation directions, small and large angles,
+    magnifying and shrinking ratios, through the forced TMA path; exact = bit-equal, fast = +-1 LSB."""
+    sz = (368, 250)                                     # 368 * 3 bytes is a multiple of 16
+    intr = camera_for(sz)
+    view = ((0.15, -0.1, rz), (-8.0, -12.0, 30.0))
+    ch, ip, ratio, axs = _rect_case(intr, sz, ratio_scale=ratio_scale, view=view)
+    c = _calib(cc, intr, [view])
+    rng = np.random.default_rng(77)
+    frames = rng.integers(0, 256, (3, sz[1], sz[0], 3), dtype=np.uint8)
+    ref = oc.rectify_u8c3(ch, 1.0 / ratio, axs, frames, fill=(9, 8, 7))
+    try:
+        got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(9, 8, 7), gather="tma").cpu().numpy()
+    except cc.CamcalError:                              # footprint too large to stage at this angle: the direct path serves it
+        got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(9, 8, 7)).cpu().numpy()
+    assert np.array_equal(got, ref)
+    fast = cc.warp(c, 0, _dev(frames), ratio, axs, fill=(9, 8, 7), coord="f32").cpu().numpy()
+    inb = np.any(ref != np.array((9, 8, 7), dtype=np.uint8), axis=-1)
+    # the FP32 map may move a sample across the frame edge: compare where both sampled
+    both = inb & np.any(fast != np.array((9, 8, 7), dtype=np.uint8), axis=-1)
+    assert both.mean() > 0.02
+    d = np.abs(fast[both].astype(np.int16) - ref[both].astype(np.int16))
+    assert d.max() <= 2 and (d > 1).mean() < 1e-3       # +-1 LSB; a 1e-3 px map error on white noise can add one more, rarely
+    assert (inb != np.any(fast != np.array((9, 8, 7), dtype=np.uint8), axis=-1)).mean() < 2e-3
+
+
 def test_rectify_tilted_views_staged_and_fallback(cc, example_fit):
     """The reference's own example views are tilted up to 0.8 rad: tile footprints reach 75 x 75
     texels, some exceed the staged box -> those pixels take the direct path inside the TMA
