@@ -87,6 +87,10 @@ struct DeviceGuard {
 #define CC_GUARD DeviceGuard _cc_guard
 
 // ---- host pipeline ---------------------------------------------------------------
+static int ensure_stream(cc_ctx* ctx, int k) {
+    if (!ctx->pipe_stream[k]) CC_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[k], cudaStreamNonBlocking));
+    return CC_OK;
+}
 static int ensure_slot(cc_ctx* ctx, int k, size_t in_bytes, size_t out_bytes) {
     if (!ctx->pipe_stream[k]) CC_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[k], cudaStreamNonBlocking));
     if (ctx->pipe_in_bytes[k] < in_bytes) {
@@ -417,11 +421,11 @@ int cc_rectify_u8c3(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doubl
 // Frames with DIFFERENT views in one call: the reference's plot loop rectifies every calibration
 // image with its own extrinsic (src/plot_calibration.jl:36-42).  frames [v * frames_per_view,
 // (v + 1) * frames_per_view) use views[v], ratios[v], axs_mins[2v .. 2v+1].  Every view is one
-// launch on `stream` with its own cached tile plan.
+// launch with its own cached tile plan.
 template <typename P, typename F>
 static int rectify_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, int nviews, const double* ratios,
                          const int64_t* axs_mins, const P* src, P* dst, int sz1, int sz2, size_t pitch,
-                         size_t frame_stride, int frames_per_view, int channels, F launch) {
+                         size_t frame_stride, int frames_per_view, int channels, cudaStream_t stream, F launch) {
     CC_REQUIRE(ctx && intr && (nviews == 0 || (views && ratios && axs_mins)), "NULL argument");
     CC_REQUIRE(nviews >= 0 && frames_per_view >= 0, "bad counts");
     CC_REQUIRE((long long)nviews * frames_per_view <= 65535, "at most 65535 frames per call");
@@ -435,13 +439,39 @@ static int rectify_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views,
     CC_REQUIRE(nviews * frames_per_view <= 1 || frame_stride >= pitch * (size_t)(sz2 - 1) + sz1, "frames overlap");
     CC_GUARD;
     if ((rc = enter(ctx))) return rc;
-    for (int v = 0; v < nviews && frames_per_view > 0; ++v) {
+    if (nviews == 0 || frames_per_view == 0) return CC_OK;
+    // One launch per view.  On a single stream the launches serialise: every persistent kernel ramps up
+    // and drains alone (a 1080p frame is ~15 us of launch + tail for ~5 us of work).  The views are
+    // therefore spread round-robin over the context's side streams, forked from and joined to `stream`
+    // with events, so consecutive views overlap.
+    const int lanes = std::min<int>(cc_ctx::NSLOT, nviews);
+    cudaEvent_t fork = nullptr, join[cc_ctx::NSLOT] = {};
+    if (lanes > 1) {
+        CC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CC_CUDA(cudaEventRecord(fork, stream));
+        for (int k = 0; k < lanes; ++k) {
+            if ((rc = ensure_stream(ctx, k))) return rc;
+            CC_CUDA(cudaStreamWaitEvent(ctx->pipe_stream[k], fork, 0));
+        }
+    }
+    for (int v = 0; v < nviews; ++v) {
         ChainD ch;
         build_chain(intr, views + v, &ch);
         const size_t off = (size_t)v * frames_per_view * frame_stride * channels;
-        if ((rc = launch(ch, ratios[v], axs_mins + 2 * v, src + off, dst + off))) return rc;
+        cudaStream_t st = lanes > 1 ? ctx->pipe_stream[v % lanes] : stream;
+        if ((rc = launch(ch, ratios[v], axs_mins + 2 * v, src + off, dst + off, st))) break;
     }
-    return CC_OK;
+    if (lanes > 1) {                                  // join even after an error: nothing stays forked
+        for (int k = 0; k < lanes; ++k) {
+            if (cudaEventCreateWithFlags(&join[k], cudaEventDisableTiming) == cudaSuccess) {
+                cudaEventRecord(join[k], ctx->pipe_stream[k]);
+                cudaStreamWaitEvent(stream, join[k], 0);
+                cudaEventDestroy(join[k]);            // released once the wait has consumed it
+            }
+        }
+        cudaEventDestroy(fork);
+    }
+    return rc;
 }
 
 extern "C" {
@@ -450,10 +480,10 @@ int cc_rectify_f32c1_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* view
                            const int64_t* axs_mins, const float* src, float* dst, int sz1, int sz2, size_t pitch,
                            size_t frame_stride, int frames_per_view, float fill, unsigned flags, void* stream) {
     return rectify_views(ctx, intr, views, nviews, ratios, axs_mins, src, dst, sz1, sz2, pitch, frame_stride,
-                         frames_per_view, 1,
-                         [&](const ChainD& ch, double ratio, const int64_t* axs, const float* s, float* d) {
+                         frames_per_view, 1, (cudaStream_t)stream,
+                         [&](const ChainD& ch, double ratio, const int64_t* axs, const float* s, float* d, cudaStream_t st) {
                              return launch_rectify_f32c1(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
-                                                         frames_per_view, fill, flags, (cudaStream_t)stream);
+                                                         frames_per_view, fill, flags, st);
                          });
 }
 
@@ -463,10 +493,10 @@ int cc_rectify_u8c3_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views
                           void* stream) {
     CC_REQUIRE(fill != nullptr, "fill is NULL");
     return rectify_views(ctx, intr, views, nviews, ratios, axs_mins, src, dst, sz1, sz2, pitch, frame_stride,
-                         frames_per_view, 3,
-                         [&](const ChainD& ch, double ratio, const int64_t* axs, const uint8_t* s, uint8_t* d) {
+                         frames_per_view, 3, (cudaStream_t)stream,
+                         [&](const ChainD& ch, double ratio, const int64_t* axs, const uint8_t* s, uint8_t* d, cudaStream_t st) {
                              return launch_rectify_u8c3(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
-                                                        frames_per_view, fill, flags, (cudaStream_t)stream);
+                                                        frames_per_view, fill, flags, st);
                          });
 }
 
