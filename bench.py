@@ -481,6 +481,34 @@ def extras(cc, torch, dev, c2cal, args):
             "note": "64 frames, 64 different views, one call (64 launches, tile plans cached after the first call); "
                     "first_call_ms includes building and uploading the 64 tile plans on the host"}
     del src, dst
+    # ingest: compressed JPEG bytes -> device frames -> the views call, nothing returns to
+    # the host in between (the reference: FileIO.load + warp per file, src/plot_calibration.jl:36-42)
+    try:
+        import cv2
+        yy, xx = np.mgrid[0:sz[0], 0:sz[1]]
+        stills = [np.clip(np.stack([127 + 100 * np.sin(xx / (37.0 + i)) * np.cos(yy / 53.0), 127 + 90 * np.cos(xx / 71.0 + i),
+                                    60 + 0.09 * xx + 0 * yy], -1), 0, 255).astype(np.uint8) for i in range(8)]
+        blobs = [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 92])[1].tobytes() for im in stills]
+        fr8 = cc.load_jpegs(blobs)
+        out8 = torch.empty_like(fr8)
+        def ingest():
+            cc.load_jpegs(blobs, out=fr8)
+            cc.warp_views(calv, list(range(8)), fr8, [ratio] * 8, [axs] * 8, coord="f64", out=out8)
+        for _ in range(2):
+            ingest()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ingest()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 5
+        ex["ingest_jpeg_8x1080p"] = {"mpix_per_s": 8 * sz[0] * sz[1] / dt / 1e6, "ms": dt * 1e3,
+                                     "compressed_mb": sum(len(b) for b in blobs) / 1e6,
+                                     "api": "cc_jpeg_decode_u8c3 (nvJPEG + transposition kernel) -> cc_rectify_u8c3_views, wall clock",
+                                     "note": "decode-bound (nvJPEG hybrid backend: Huffman on the host); library code, not a roofline line"}
+        del fr8, out8
+    except Exception as e:                    # cv2 or libnvjpeg missing: the ingest line is optional
+        ex["ingest_jpeg_8x1080p"] = {"unavailable": str(e)[:120]}
     wl = WORKLOADS["c3"]
     rng = np.random.default_rng(7)
     nv, nc = 10_000, 280

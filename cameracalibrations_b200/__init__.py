@@ -15,7 +15,7 @@ from .shard import shard_range, shard_frames      # pure host logic: importable 
 _LAZY = {
     "_lib": ("CamcalError", "Context", "context", "device_count", "LIB_PATH", "EXPORTS"),
     "calibration": ("Calibration", "rectification", "get_ratio", "get_axes", "image_transformations", "warp",
-                    "warp_views", "rectify_map", "reproj_jtj", "calculate_errors", "allreduce_shared", "save", "load", "views_tensor"),
+                    "warp_views", "rectify_map", "load_jpegs", "jpeg_info", "reproj_jtj", "calculate_errors", "allreduce_shared", "save", "load", "views_tensor"),
     "fit": ("fit", "detect_fit", "fit_model"),
     "lm": ("lm_fit", "lm_fit_host", "lm_fit_device", "initial_guess", "initial_guess_device"),
 }
@@ -34,7 +34,7 @@ RowCol = "SVector{2}: (row, col) -- arrays of shape (..., 2)"
 XYZ = "SVector{3}: (x, y, z) -- arrays of shape (..., 3)"
 
 __all__ = ["Calibration", "rectification", "fit", "detect_fit", "get_ratio", "get_axes",
-           "image_transformations", "warp", "rectify_map", "reproj_jtj", "calculate_errors", "save",
+           "image_transformations", "warp", "warp_views", "rectify_map", "load_jpegs", "jpeg_info", "reproj_jtj", "calculate_errors", "save",
            "load", "views_tensor", "shard_range", "shard_frames", "CamcalError", "Context", "context",
            "device_count", "RowCol", "XYZ", "lm_fit", "lm_fit_host", "lm_fit_device", "initial_guess",
            "initial_guess_device", "allreduce_shared", "fit_model"]

@@ -90,6 +90,8 @@ _SIGS = {
     "cc_rectify_u8c3_views": (_i, [_vp, _pI, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _sz, _sz, _i, _u8p, _u, _vp]),
     "cc_rectify_map_f64": (_i, [_vp, _pI, _pV, _d, _i64p, _vp, _vp, _i, _i, _sz, _vp]),
     "cc_rectify_map_f32": (_i, [_vp, _pI, _pV, _d, _i64p, _vp, _vp, _i, _i, _sz, _vp]),
+    "cc_jpeg_info": (_i, [_vp, _sz, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "cc_jpeg_decode_u8c3": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _sz, _sz, _vp]),
     "cc_get_ratio": (_i, [_vp, _vp, _i, _i, _d, C.POINTER(_d)]),
     "cc_get_axes": (_i, [_d, _d, _i, _i, _i, _i, _i64p]),
     "cc_reproj_jtj_f64": (_i, [_vp, _pI, _d, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -311,6 +311,40 @@ def warp_views(c: Calibration, extrinsics, frames, ratios, axs_mins, fill=None, 
     return out
 
 
+def jpeg_info(data: bytes):
+    """(sz1, sz2, channels) = (rows, columns, components) of a JPEG stream; header parse only."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    a, b, ch = C.c_int(), C.c_int(), C.c_int()
+    check(lib.cc_jpeg_info(buf, C.c_size_t(len(data)), C.byref(a), C.byref(b), C.byref(ch)))
+    return a.value, b.value, ch.value
+
+
+def load_jpegs(datas, device=None, out=None):
+    """Device-side `RGB.(FileIO.load(file))` for a list of JPEG files (src/plot_calibration.jl:37):
+    the compressed bytes go to the GPU, the decoded frames never come back.  datas: list of bytes
+    objects (or file names), all the same size.  Returns a CUDA uint8 tensor (n, sz2, sz1, 3) -- the
+    u8c3 frame layout that warp() / warp_views() take."""
+    blobs = []
+    for d in datas:
+        if isinstance(d, (str, bytes.__class__)) and not isinstance(d, (bytes, bytearray, memoryview)):
+            with open(d, "rb") as f:
+                d = f.read()
+        blobs.append(bytes(d))
+    if not blobs:
+        raise ValueError("no images")
+    sz1, sz2, _ = jpeg_info(blobs[0])
+    dev = _default_device() if device is None else int(device)
+    if out is None:
+        out = torch.empty((len(blobs), sz2, sz1, 3), dtype=torch.uint8, device=f"cuda:{dev}")
+    bufs = [(C.c_uint8 * len(b)).from_buffer_copy(b) for b in blobs]
+    ptrs = (C.c_void_p * len(bufs))(*[C.addressof(b) for b in bufs])
+    lens = (C.c_size_t * len(bufs))(*[len(b) for b in blobs])
+    check(lib.cc_jpeg_decode_u8c3(_lib.context(dev).handle, ptrs, lens, len(bufs), _t_ptr(out), sz1, sz2,
+                                  C.c_size_t(sz1), C.c_size_t(sz1 * sz2), _stream_ptr(dev)))
+    torch.cuda.current_stream(dev).synchronize()      # the compressed host buffers die with this frame
+    return out
+
+
 def rectify_map(c: Calibration, extrinsic, ratio: float, axs_min, sz, device=None, coord: str = "f64"):
     """Source (row, col) sampled by every output pixel as two (sz2, sz1) CUDA tensors: FP64 (the
     reference's map) or, coord="f32", the FP32 map of the fast path."""

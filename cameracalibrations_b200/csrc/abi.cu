@@ -283,6 +283,7 @@ int cc_ctx_destroy(cc_ctx* ctx) {
     comm_free(ctx);
     rectify_free_plans(ctx);
     rectify_free_sched(ctx);
+    ingest_free(ctx);
     delete ctx;
     return CC_OK;
 }
@@ -498,6 +499,26 @@ int cc_rectify_u8c3_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views
                              return launch_rectify_u8c3(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
                                                         frames_per_view, fill, flags, st);
                          });
+}
+
+int cc_jpeg_info(const uint8_t* jpeg, size_t length, int* sz1, int* sz2, int* channels) {
+    CC_REQUIRE(jpeg && length > 0, "NULL / empty JPEG stream");
+    return jpeg_info(jpeg, length, sz1, sz2, channels);
+}
+
+int cc_jpeg_decode_u8c3(cc_ctx* ctx, const uint8_t* const* jpegs, const size_t* lengths, int n, uint8_t* dst,
+                        int sz1, int sz2, size_t pitch, size_t frame_stride, void* stream) {
+    CC_REQUIRE(ctx != nullptr, "NULL context");
+    CC_REQUIRE(n >= 0, "negative image count");
+    if (n == 0) return CC_OK;
+    CC_REQUIRE(jpegs && lengths && dst, "NULL argument");
+    CC_REQUIRE(sz1 > 0 && sz2 > 0 && pitch >= (size_t)sz1, "bad frame size / pitch");
+    CC_REQUIRE(n <= 1 || frame_stride >= pitch * (size_t)(sz2 - 1) + sz1, "frames overlap");
+    for (int i = 0; i < n; ++i) CC_REQUIRE(jpegs[i] && lengths[i] > 0, "NULL / empty JPEG stream");
+    int rc;
+    CC_GUARD;
+    if ((rc = enter(ctx))) return rc;
+    return jpeg_decode_u8c3(ctx, jpegs, lengths, n, dst, sz1, sz2, pitch, frame_stride, (cudaStream_t)stream);
 }
 
 int cc_rectify_f32c1_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, double ratio,

@@ -28,6 +28,10 @@ void build_chain(const cc_intr* in, const cc_view* vw, ChainD* out);
 void narrow_chain(const ChainD& d, ChainF* f);
 void rectify_free_plans(struct ::cc_ctx* ctx);
 void rectify_free_sched(struct ::cc_ctx* ctx);
+void ingest_free(struct ::cc_ctx* ctx);
+int jpeg_info(const uint8_t* data, size_t length, int* sz1, int* sz2, int* channels);
+int jpeg_decode_u8c3(struct ::cc_ctx* ctx, const uint8_t* const* jpegs, const size_t* lengths, int n, uint8_t* dst,
+                     int sz1, int sz2, size_t pitch, size_t frame_stride, cudaStream_t st);
 void comm_free(struct ::cc_ctx* ctx);
 void lm_free_workspace(struct ::cc_ctx* ctx);
 
@@ -71,6 +75,8 @@ struct cc_ctx {
     unsigned long long collectives;       // all-reduces issued so far
     // workspace of the device-resident LM loop (lm.cu: LmWorkspace), grown on demand
     void* lm_ws;
+    // nvJPEG handle / state / raster scratch of the image ingest (ingest.cu: Ingest), created on first use
+    void* ingest;
 };
 
 #define CC_CUDA(call)                                                     \

@@ -181,6 +181,22 @@ int cc_rectify_map_f32(cc_ctx *ctx, const cc_intr *intr, const cc_view *view, do
                        const int64_t axs_min[2], float *map_row, float *map_col, int sz1,
                        int sz2, size_t pitch, void *stream);
 
+/* ---- image-file ingest on the device (the step upstream of rectification) ----------
+ * The reference reads every calibration image with FileIO.load and converts it to RGB before warp
+ * (src/plot_calibration.jl:37; also src/detect_fit.jl:6,64).  cc_jpeg_decode_u8c3 takes the
+ * COMPRESSED bytes (host pointers) of n baseline JPEG streams and leaves the decoded frames in
+ * device memory in the u8c3 layout above -- element (r, c) of frame i at
+ * dst[((i * frame_stride) + c * pitch + r) * 3], i.e. the memory of the Julia array RGB.(load(file)) --
+ * ready for cc_rectify_u8c3 / cc_rectify_u8c3_views on the same stream.  Decoding is nvJPEG (CUDA
+ * toolkit library, resolved at run time: without libnvjpeg.so.12 -> CC_ERR_UNSUPPORTED); the
+ * raster -> frame transposition is a kernel of this library.  Grey JPEGs decode to R = G = B.
+ * sz1 = image rows (height), sz2 = image columns (width); every stream must have that size.
+ * cc_jpeg_info parses the header only: rows, columns, components (nvJPEG still needs a CUDA device). */
+int cc_jpeg_info(const uint8_t *jpeg, size_t length, int *sz1, int *sz2, int *channels);
+int cc_jpeg_decode_u8c3(cc_ctx *ctx, const uint8_t *const *jpegs, const size_t *lengths, int n,
+                        uint8_t *dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
+                        void *stream);
+
 /* get_ratio / get_axes (src/plot_calibration.jl:1-13): tiny host-side helpers so a
  * binding needs nothing else to drive cc_rectify_*.  corners: (a, b) at [a + n1*b]. */
 int cc_get_ratio(const double *rows, const double *cols, int n1, int n2,

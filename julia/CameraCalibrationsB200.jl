@@ -177,6 +177,31 @@ function warp_views(d::DeviceCalibration, imgs::Array{Float32,3}, ratios::Vector
     out
 end
 
+# ---- image ingest on the device: RGB.(FileIO.load(file)) for JPEG files, src/plot_calibration.jl:37 --
+# The compressed bytes go to the GPU (nvJPEG + a transposition kernel inside the library); the result is a
+# DEVICE pointer to (3, sz1, sz2, n) bytes -- the u8c3 layout cc_rectify_u8c3[_views] take -- so a plot loop
+# over JPEG files never holds decoded pixels on the host.  `dst` comes from the caller's device allocator
+# (CUDA.jl's CuArray{UInt8,4}(undef, 3, sz1, sz2, n) works: pass pointer(dst)).
+function jpeg_info(bytes::Vector{UInt8})
+    sz1 = Ref{Cint}(0); sz2 = Ref{Cint}(0); ch = Ref{Cint}(0)
+    check(ccall((:cc_jpeg_info, libcamcal), Cint, (Ptr{UInt8}, Csize_t, Ref{Cint}, Ref{Cint}, Ref{Cint}),
+                bytes, length(bytes), sz1, sz2, ch))
+    (Int(sz1[]), Int(sz2[]), Int(ch[]))
+end
+function load_jpegs!(dst::Ptr{UInt8}, files::Vector{String}; stream::Ptr{Cvoid} = C_NULL)
+    blobs = [read(f) for f in files]
+    sz1, sz2, _ = jpeg_info(blobs[1])
+    GC.@preserve blobs begin
+        ptrs = [pointer(b) for b in blobs]
+        lens = Csize_t[length(b) for b in blobs]
+        check(ccall((:cc_jpeg_decode_u8c3, libcamcal), Cint,
+                    (Ptr{Cvoid}, Ptr{Ptr{UInt8}}, Ptr{Csize_t}, Cint, Ptr{UInt8}, Cint, Cint, Csize_t, Csize_t, Ptr{Cvoid}),
+                    context().handle, ptrs, lens, length(blobs), dst, sz1, sz2, sz1, sz1 * sz2, stream))
+        check(ccall((:cc_ctx_synchronize, libcamcal), Cint, (Ptr{Cvoid},), context().handle))   # blobs may be freed after this
+    end
+    (sz1, sz2, length(blobs))
+end
+
 # ---- multi-GPU: one Julia process per GPU (Distributed / MPI), NCCL inside the library ------------
 # rank 0:  id = comm_unique_id();  ship the 128 bytes to the other ranks (MPI.Bcast!, a file, ...)
 # all:     comm_init_rank(nranks, rank, id)

@@ -714,3 +714,57 @@ def test_save_load_round_trip(cc, tmp_path, example_fit):
     assert c2.extrinsics == c.extrinsics and c2.scale == c.scale
     p = np.array([[10.0, 20.0], [300.0, 400.0]])
     assert np.array_equal(c(p, 2), c2(p, 2))
+
+
+# ------------------------------------------------------------------ ingest
+def test_jpeg_ingest_feeds_the_plot_loop(cc, example_fit):
+    """src/plot_calibration.jl:36-42 on the device: compressed JPEG bytes -> cc_jpeg_decode_u8c3 (nvJPEG +
+    the raster->frame transposition kernel) -> cc_rectify_u8c3_views, nothing returns to the host in
+    between.  The decoder is checked against cv2.imdecode (libjpeg: IDCT / upsampling differ by a few
+    LSB), the rectification of the DECODED frames is bit-equal to the oracle on the same bytes."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(21)
+    h, w = 250, 368                                     # rows, columns
+    yy, xx = np.mgrid[0:h, 0:w]
+    imgs = []
+    for i in range(3):                                  # smooth content: JPEG keeps it within a few LSB
+        im = np.stack([127 + 100 * np.sin(xx / (17.0 + i) + i) * np.cos(yy / 23.0),
+                       127 + 90 * np.cos(xx / 31.0) * np.sin(yy / (13.0 + 2 * i)),
+                       (xx * 255.0 / w + yy * 0.2 * i) % 256 * 0 + 60 + 0.5 * xx], axis=-1)
+        imgs.append(np.clip(im + rng.normal(0, 2, im.shape), 0, 255).astype(np.uint8))
+    enc = [cv2.imencode(".jpg", im[:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes() for im in imgs]   # cv2 is BGR
+    assert cc.jpeg_info(enc[0]) == (h, w, 3)
+    try:
+        frames = cc.load_jpegs(enc)
+    except cc.CamcalError as e:
+        if "libnvjpeg" in str(e):
+            pytest.skip("libnvjpeg.so.12 not on this box")
+        raise
+    assert tuple(frames.shape) == (3, w, h, 3) and frames.is_cuda
+    got = frames.cpu().numpy()
+    for i in range(3):
+        ref = cv2.imdecode(np.frombuffer(enc[i], np.uint8), cv2.IMREAD_COLOR)[:, :, ::-1]      # (h, w, RGB)
+        d = np.abs(got[i].transpose(1, 0, 2).astype(np.int16) - ref.astype(np.int16))           # frame memory is [c][r]
+        assert d.max() <= 12 and d.mean() < 2.0, (i, d.max(), d.mean())   # 4:2:0 chroma upsampling differs between the decoders
+        assert np.abs(got[i].transpose(1, 0, 2).astype(np.int16) - imgs[i].astype(np.int16)).mean() < 4.0
+    # grey stream: R = G = B, like RGB.(load(file))
+    g = cv2.imencode(".jpg", imgs[0][:, :, 1], [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes()
+    assert cc.jpeg_info(g) == (h, w, 1)
+    gf = cc.load_jpegs([g]).cpu().numpy()[0]
+    assert np.array_equal(gf[..., 0], gf[..., 1]) and np.array_equal(gf[..., 1], gf[..., 2])
+    assert np.abs(gf[..., 0].T.astype(np.int16) - imgs[0][:, :, 1].astype(np.int16)).mean() < 3.0
+    # decoded frames straight into the views call (three different extrinsics), against the oracle
+    sz = (h, w)
+    intr = camera_for(sz)
+    views = [((0.15, -0.1, rz), (-8.0, -12.0, 30.0)) for rz in (0.02, 0.3, -0.2)]
+    c = _calib(cc, intr, views)
+    ras = [_rect_case(intr, sz, view=v) for v in views]
+    out = cc.warp_views(c, [0, 1, 2], frames, [r[2] for r in ras], [r[3] for r in ras], fill=(0, 0, 0)).cpu().numpy()
+    for i, (ch, _, ratio, axs) in enumerate(ras):
+        ref = oc.rectify_u8c3(ch, 1.0 / ratio, axs, got[i:i + 1], fill=(0, 0, 0))[0]
+        assert np.array_equal(out[i], ref), i
+    # wrong size and garbage are errors, not crashes
+    with pytest.raises(cc.CamcalError):
+        cc.load_jpegs([enc[0], cv2.imencode(".jpg", imgs[0][:100])[1].tobytes()])
+    with pytest.raises(cc.CamcalError):
+        cc.jpeg_info(b"not a jpeg at all, just bytes")
