@@ -250,8 +250,9 @@ void cco_rectify_coord(const cco_chain *ch, double inv_ratio, long long I1,
 }
 
 /* Bilinear rule of warp() -> Interpolations BSpline(Linear()) OnGrid with a
- * filled extrapolation (src/plot_calibration.jl:40; third-party, PARITY
- * UNPINNED): sample at (row, col) in the image's own 1-based axes;
+ * filled extrapolation (src/plot_calibration.jl:40; third-party; pinned to
+ * scipy.ndimage.map_coordinates and cv2.remap, not to Julia output: PARITY
+ * UNPINNED against the reference itself): sample at (row, col) in the image's own 1-based axes;
  * outside [1,n] on either axis -> fill; i = floor(x), pulled back by one when
  * i > n-1 (x == n); delta = x - i; weights (1-delta, delta).
  * Returns 0 if out of bounds, else fills i0 (0-based), d. */

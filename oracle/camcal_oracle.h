@@ -15,7 +15,11 @@
  * src/detect_fit.jl:47), (3) a numpy twin that finds the cubic root the way
  * src/meta.jl:53-55 does (companion-matrix eigenvalues).  The warp's third-party
  * bilinear rule (ImageTransformations/Interpolations, src/plot_calibration.jl:40)
- * has no reference test at all: that part is "parity unpinned".
+ * has no reference test at all; since round 2 it is pinned to two independent
+ * stand-ins (scipy.ndimage.map_coordinates(order=1): index, weights, edges, fill;
+ * cv2.remap: tap selection -- tests/test_oracle.py), but NOT to output of the real
+ * Julia package: against the reference itself that part stays "parity unpinned"
+ * until julia/make_golden.jl has been run (tests/test_julia_golden.py consumes it).
  *
  * Every function cites the reference lines it follows.  The ORDER OF FLOATING
  * POINT OPERATIONS below is normative for the bit-exact FP64 remap parity tests:

@@ -12,9 +12,41 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 go, out = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles", "r2")
 os.makedirs(out, exist_ok=True)
 
-for a, b in (("r2_bench.json", "bench.json"), ("r2_bench_ref.json", "bench_ref.json")):
+def json_line(path):
+    for l in open(path):
+        if l.startswith("{"):
+            return l
+    return None
+
+benches = {}
+for a, b in (("r2_bench.json", "bench.json"), ("r2_bench_ref.json", "bench_ref.json"), ("r2_bench_n2.json", "bench_n2.json"),
+             ("r2_bench_n4.json", "bench_n4.json"), ("r2_bench_n8.json", "bench_n8.json")):
     if os.path.exists(os.path.join(go, a)):
-        shutil.copy(os.path.join(go, a), os.path.join(out, b))
+        l = json_line(os.path.join(go, a))
+        if l:
+            open(os.path.join(out, b), "w").write(l)
+            benches[b] = json.loads(l)
+if os.path.exists(os.path.join(go, "r2_topo.txt")):
+    shutil.copy(os.path.join(go, "r2_topo.txt"), os.path.join(out, "topo_8gpu.txt"))
+
+# ---- 1/2/4/8 GPUs: the named multi-GPU configs and the host-link ceiling, one table
+rows = [(n, benches.get(f)) for n, f in ((1, "bench.json"), (2, "bench_n2.json"), (4, "bench_n4.json"), (8, "bench_n8.json"))]
+if all(d for _, d in rows):
+    with open(os.path.join(out, "scaling_summary.txt"), "w") as f:
+        f.write("# python bench.py (N=1) / torchrun ... bench.py --gpus N --steps 20 --warmup 3 on one 8 x B200 box (N=1: its own 1-GPU box)\n")
+        f.write("# device-resident values are CUDA-event times, max over ranks; e2e and the stream are wall clock with host buffers\n")
+        f.write("# link = pinned<->device copies, both directions at once, EVERY rank at once (GB/s per direction per GPU)\n")
+        f.write(f"{'N':>2s} {'C2 Gpix/s':>10s} {'frac':>6s} {'e2e Gpix/s':>11s} {'link/GPU':>9s} {'link sum':>9s} {'e2e/link':>9s} "
+                f"{'C3 stream':>10s} {'C3 dev f64':>11s} {'C3 dev f32':>11s} {'C4 f64 Gpt/s':>13s} {'C4 f32':>8s} {'C5 JtJ us':>10s} {'LM us/it':>9s}\n")
+        for n, d in rows:
+            e, x = d["e2e"], d["extras"]
+            lk = e["link_ceiling"]["duplex_gbs_per_dir_per_gpu"]
+            f.write(f"{n:2d} {d['value'] / 1e3:10.1f} {d['roofline']['frac']:6.3f} {e['value'] / 1e3:11.2f} {lk:9.1f} {lk * n:9.1f} {e['link_frac']:9.3f} "
+                    f"{x['c3_stream_f64']['mpix_per_s_e2e'] / 1e3:10.2f} {x['c3_device_f64']['mpix_per_s'] / 1e3:11.1f} {x['c3_device_f32']['mpix_per_s'] / 1e3:11.1f} "
+                    f"{x['c4_img2world_f64_100M']['gpt_per_s']:13.1f} {x['c4_img2world_f32_100M']['gpt_per_s']:8.1f} "
+                    f"{x['c5_reproj_jtj_10k_views']['ms'] * 1e3:10.1f} {x['c5_lm_iterations_10k_views']['us_per_iteration']:9.1f}\n")
+        f.write("# C2 / C3 device: weak scaling (every rank its own batch of the same size); C3 stream: 4096 frames, C4: 100 M points,\n")
+        f.write("# C5: 10k views -- each split over the ranks (strong); C5 has the 21-double NCCL all-reduce inside the timed region for N > 1\n")
 
 # ---- launch list ------------------------------------------------------------------------------------
 src = os.path.join(go, "r2_launches.csv")
