@@ -97,6 +97,7 @@ _SIGS = {
     "cc_reproj_jtj_f64": (_i, [_vp, _pI, _d, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "cc_reproj_jtj_f64_host": (_i, [_vp, _pI, _d, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "cc_calculate_errors_f64": (_i, [_vp, _pI, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "cc_calculate_errors_f64_host": (_i, [_vp, _pI, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "cc_lm_schur_f64": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
     "cc_lm_update_f64": (_i, [_vp, _vp, _vp, _d, _u, _vp, _vp, _i, _vp, _vp, _vp]),
     "cc_lm_fit_f64_host": (_i, [_vp, _pI, _d, _u, _vp, _i, _vp, _vp, _i, _i, _d, C.POINTER(_d), C.POINTER(_i)]),
@@ -108,6 +109,9 @@ _SIGS = {
     "cc_comm_size": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "cc_comm_nccl_version": (_i, [C.POINTER(_i)]),
     "cc_allreduce_shared": (_i, [_vp, _vp, _sz, _vp]),
+    "cc_ctx_create_group": (_i, [_i, C.POINTER(_i), C.POINTER(_vp)]),
+    "cc_ctx_destroy_group": (_i, [_i, C.POINTER(_vp)]),
+    "cc_allreduce_shared_group": (_i, [C.POINTER(_vp), _i, C.POINTER(_vp), _sz, C.POINTER(_vp)]),
     "cc_ctx_collective_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
 }
 

@@ -696,6 +696,49 @@ int cc_calculate_errors_f64(cc_ctx* ctx, const cc_intr* intr, const cc_view* vie
                               inverse_samples, sums, (cudaStream_t)stream);
 }
 
+// host arrays in, the four raw sums out: what calculate_errors (src/buildcalibrations.jl:37-67) needs from a
+// caller that holds the detections on the host, like the reference does
+int cc_calculate_errors_f64_host(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, int nviews,
+                                 const double* obj, const double* img, int n1, int n2, const double* inv_rows,
+                                 const double* inv_cols, int inverse_samples, double* sums) {
+    CC_REQUIRE(ctx && intr && sums, "NULL argument");
+    CC_REQUIRE(nviews >= 0 && n1 >= 1 && n2 >= 1 && inverse_samples >= 0, "bad sizes");
+    CC_REQUIRE(nviews == 0 || (views && obj && img), "NULL host pointer");
+    CC_REQUIRE(inverse_samples == 0 || nviews == 0 || (inv_rows && inv_cols), "NULL sample pointer");
+    CC_REQUIRE(intr->checker_size != 0.0 && intr->frow != 0.0 && intr->fcol != 0.0, "bad intrinsics");
+    CC_GUARD;
+    int rc = enter(ctx);
+    if (rc) return rc;
+    const size_t nv = (size_t)(nviews > 0 ? nviews : 1), nc = (size_t)n1 * n2;
+    const size_t b_views = round_up(nv * sizeof(cc_view), 256);
+    const size_t b_obj = round_up(nc * 3 * sizeof(double), 256);
+    const size_t b_img = round_up(nv * nc * 2 * sizeof(double), 256);
+    const size_t b_inv = round_up(nv * (size_t)std::max(inverse_samples, 1) * sizeof(double), 256);
+    if ((rc = ensure_slot(ctx, 0, b_views + b_obj + b_img + 2 * b_inv, 256))) return rc;
+    cudaStream_t st = ctx->pipe_stream[0];
+    uint8_t* din = static_cast<uint8_t*>(ctx->pipe_in[0]);
+    cc_view* d_views = reinterpret_cast<cc_view*>(din);
+    double* d_obj = reinterpret_cast<double*>(din + b_views);
+    double* d_img = reinterpret_cast<double*>(din + b_views + b_obj);
+    double* d_ir = reinterpret_cast<double*>(din + b_views + b_obj + b_img);
+    double* d_ic = reinterpret_cast<double*>(din + b_views + b_obj + b_img + b_inv);
+    double* d_sums = static_cast<double*>(ctx->pipe_out[0]);
+    if (nviews > 0) {
+        CC_CUDA(cudaMemcpyAsync(d_views, views, (size_t)nviews * sizeof(cc_view), cudaMemcpyHostToDevice, st));
+        CC_CUDA(cudaMemcpyAsync(d_obj, obj, nc * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CC_CUDA(cudaMemcpyAsync(d_img, img, (size_t)nviews * nc * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (inverse_samples > 0) {
+            CC_CUDA(cudaMemcpyAsync(d_ir, inv_rows, (size_t)nviews * inverse_samples * sizeof(double), cudaMemcpyHostToDevice, st));
+            CC_CUDA(cudaMemcpyAsync(d_ic, inv_cols, (size_t)nviews * inverse_samples * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+    }
+    if ((rc = launch_calc_errors(ctx, intr, d_views, nviews, d_obj, d_img, n1, n2, d_ir, d_ic, inverse_samples, d_sums, st)))
+        return rc;
+    CC_CUDA(cudaMemcpyAsync(sums, d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CC_CUDA(cudaStreamSynchronize(st));
+    return CC_OK;
+}
+
 // ---- Levenberg-Marquardt step -----------------------------------------------------
 int cc_lm_schur_f64(cc_ctx* ctx, const double* per_view, int nviews, double lambda, double* yz,
                     double* schur, void* stream) {

@@ -26,6 +26,9 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
 };
 
 static NcclApi g_nccl;
@@ -45,6 +48,9 @@ static int nccl_load() {
     *(void**)&a.AllReduce = dlsym(h, "ncclAllReduce");
     *(void**)&a.GetErrorString = dlsym(h, "ncclGetErrorString");
     *(void**)&a.GetVersion = dlsym(h, "ncclGetVersion");
+    *(void**)&a.CommInitAll = dlsym(h, "ncclCommInitAll");
+    *(void**)&a.GroupStart = dlsym(h, "ncclGroupStart");
+    *(void**)&a.GroupEnd = dlsym(h, "ncclGroupEnd");
     if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
         return set_error(CC_ERR_UNSUPPORTED, "libnccl.so.2 lacks an expected symbol");
     g_nccl = a;
@@ -131,6 +137,72 @@ int cc_allreduce_shared(cc_ctx* ctx, double* buf, size_t count, void* stream) {
     CC_REQUIRE(ctx != nullptr, "ctx is NULL");
     CC_REQUIRE(buf != nullptr || count == 0, "buffer is NULL");
     return comm_allreduce_sum(ctx, buf, count, static_cast<cudaStream_t>(stream));
+}
+
+// ---- one process, several GPUs ("cc_ctx_create(ndev, devs): owns streams, NCCL comms, scratch").
+// A single Julia session that drives all GPUs of a box creates one context per device, joined in one
+// communicator; the shared block is then summed with ONE grouped call.  Entry points that
+// synchronise internally on a collective (cc_lm_fit_f64) must be called from one host thread per
+// context; everything else is asynchronous and can be issued from one thread, device after device.
+int cc_ctx_create_group(int ndev, const int* devs, cc_ctx** ctxs) {
+    CC_REQUIRE(ndev >= 1 && devs && ctxs, "bad device list");
+    for (int i = 0; i < ndev; ++i) {
+        ctxs[i] = nullptr;
+        for (int j = 0; j < i; ++j) CC_REQUIRE(devs[i] != devs[j], "a device appears twice in the list");
+    }
+    int rc = CC_OK;
+    for (int i = 0; i < ndev && !rc; ++i) rc = cc_ctx_create(devs[i], &ctxs[i]);
+    if (!rc && ndev > 1) {
+        rc = nccl_load();
+        if (!rc && (!g_nccl.CommInitAll || !g_nccl.GroupStart || !g_nccl.GroupEnd))
+            rc = set_error(CC_ERR_UNSUPPORTED, "libnccl.so.2 lacks ncclCommInitAll / ncclGroupStart");
+        if (!rc) {
+            ncclComm_t comms[64];
+            if (ndev > 64) rc = set_error(CC_ERR_INVALID_ARG, "at most 64 devices per group");
+            else {
+                int prev = -1;
+                cudaGetDevice(&prev);
+                const ncclResult_t r = g_nccl.CommInitAll(comms, ndev, devs);
+                if (prev >= 0) cudaSetDevice(prev);
+                if (r != ncclSuccess) rc = nccl_fail(r, "ncclCommInitAll");
+                else
+                    for (int i = 0; i < ndev; ++i) { ctxs[i]->nccl_comm = comms[i]; ctxs[i]->comm_nranks = ndev; ctxs[i]->comm_rank = i; }
+            }
+        }
+    }
+    if (rc)
+        for (int i = 0; i < ndev; ++i)
+            if (ctxs[i]) { cc_ctx_destroy(ctxs[i]); ctxs[i] = nullptr; }
+    return rc;
+}
+
+int cc_ctx_destroy_group(int ndev, cc_ctx** ctxs) {
+    CC_REQUIRE(ndev >= 0 && (ndev == 0 || ctxs), "bad context list");
+    int rc = CC_OK;
+    for (int i = 0; i < ndev; ++i)
+        if (ctxs[i]) { const int r = cc_ctx_destroy(ctxs[i]); ctxs[i] = nullptr; if (r && !rc) rc = r; }
+    return rc;
+}
+
+// bufs[i] (device memory of ctxs[i]'s GPU) <- sum over i, in place, each on streams[i] (NULL: default streams)
+int cc_allreduce_shared_group(cc_ctx* const* ctxs, int ndev, double* const* bufs, size_t count, void* const* streams) {
+    CC_REQUIRE(ndev >= 1 && ctxs && bufs, "bad arguments");
+    for (int i = 0; i < ndev; ++i) {
+        CC_REQUIRE(ctxs[i] != nullptr && (bufs[i] != nullptr || count == 0), "NULL context / buffer");
+        CC_REQUIRE(ctxs[i]->comm_nranks == ndev || ndev == 1, "the contexts are not one group (cc_ctx_create_group)");
+    }
+    if (ndev == 1 || count == 0) return CC_OK;
+    ncclResult_t r = g_nccl.GroupStart();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+    for (int i = 0; i < ndev && r == ncclSuccess; ++i) {
+        r = g_nccl.AllReduce(bufs[i], bufs[i], count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctxs[i]->nccl_comm),
+                             static_cast<cudaStream_t>(streams ? streams[i] : nullptr));
+        ctxs[i]->collectives++;
+    }
+    const ncclResult_t e = g_nccl.GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+    if (e != ncclSuccess) return nccl_fail(e, "ncclGroupEnd");
+    return CC_OK;
 }
 
 int cc_comm_nccl_version(int* version) {

@@ -235,6 +235,11 @@ int cc_calculate_errors_f64(cc_ctx *ctx, const cc_intr *intr, const cc_view *vie
                             int nviews, const double *obj, const double *img, int n1, int n2,
                             const double *inv_rows, const double *inv_cols,
                             int inverse_samples, double *sums, void *stream);
+/* the same with HOST arrays (copies in, the four sums back; one synchronisation) */
+int cc_calculate_errors_f64_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *views,
+                                 int nviews, const double *obj, const double *img, int n1,
+                                 int n2, const double *inv_rows, const double *inv_cols,
+                                 int inverse_samples, double *sums);
 
 /* ---- one Levenberg-Marquardt step on those blocks (the solve OpenCV.calibrateCamera runs
  *      inside the reference's fit, src/detect_fit.jl:47; flags :40; CRITERIA
@@ -303,6 +308,16 @@ int cc_comm_nccl_version(int *version);
 /* in-place sum of `count` doubles (device) over the ranks, asynchronous on `stream`:
  * cc_reproj_jtj_f64's `shared`, cc_calculate_errors_f64's `sums`, cc_lm_schur_f64's `schur` */
 int cc_allreduce_shared(cc_ctx *ctx, double *buf, size_t count, void *stream);
+/* One process, several GPUs (a single Julia session driving the whole box): ndev contexts, one per
+ * device of devs[], joined in ONE communicator (ncclCommInitAll) -- the multi-device context of
+ * SURVEY 8b.  cc_allreduce_shared_group sums bufs[i] (device memory of ctxs[i]) over the group in
+ * place with one grouped NCCL call, each on streams[i] (streams == NULL: the default streams).
+ * Entry points that wait on a collective internally (cc_lm_fit_f64) need one host thread per
+ * context; all other calls are asynchronous and may be issued device after device from one thread. */
+int cc_ctx_create_group(int ndev, const int *devs, cc_ctx **ctxs);
+int cc_ctx_destroy_group(int ndev, cc_ctx **ctxs);
+int cc_allreduce_shared_group(cc_ctx *const *ctxs, int ndev, double *const *bufs, size_t count,
+                              void *const *streams);
 /* number of all-reduces this context has issued so far */
 int cc_ctx_collective_count(const cc_ctx *ctx, uint64_t *count);
 

@@ -218,6 +218,22 @@ allreduce_shared!(buf::Ptr{Cdouble}, count::Integer; stream::Ptr{Cvoid} = C_NULL
     check(ccall((:cc_allreduce_shared, libcamcal), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Csize_t, Ptr{Cvoid}),
                 context().handle, buf, count, stream))
 
+# One Julia session driving several GPUs: one context per device, joined in one communicator.
+struct ContextGroup
+    handles::Vector{Ptr{Cvoid}}
+end
+function ContextGroup(devs::Vector{<:Integer})
+    h = Vector{Ptr{Cvoid}}(undef, length(devs))
+    check(ccall((:cc_ctx_create_group, libcamcal), Cint, (Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}), length(devs), Cint.(devs), h))
+    g = ContextGroup(h)
+    finalizer(x -> ccall((:cc_ctx_destroy_group, libcamcal), Cint, (Cint, Ptr{Ptr{Cvoid}}), length(x), x), g.handles)   # x is the handle vector
+    g
+end
+"in-place sum over the group of `count` doubles at the device pointers `bufs[i]` (one per context)"
+allreduce_shared!(g::ContextGroup, bufs::Vector{Ptr{Cdouble}}, count::Integer) =
+    check(ccall((:cc_allreduce_shared_group, libcamcal), Cint, (Ptr{Ptr{Cvoid}}, Cint, Ptr{Ptr{Cdouble}}, Csize_t, Ptr{Ptr{Cvoid}}),
+                g.handles, length(g.handles), bufs, count, C_NULL))
+
 # ---- residual + normal-equation blocks (what calibrateCamera reduces, src/detect_fit.jl:47) ---
 function reproj_jtj(c::Calibration, aspect::Float64, objpoints::Matrix{Float64},   # 3 x ncorners
                     imgpoints::Array{Float64,3})                                    # 2 x ncorners x nviews

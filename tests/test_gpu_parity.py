@@ -702,6 +702,21 @@ def test_calculate_errors_matches_reference_bounds(cc, example_fit):
     for k, r in zip(("reprojection", "projection", "distance"), ref[:3]):
         assert abs(eps[k] - r) <= 1e-9
     assert eps["inverse"] < 1e-10 and ref[3] < 1e-10
+    # the host form of the ABI (numpy in, four raw sums out) is the same kernel behind copies
+    import ctypes as C
+    from cameracalibrations_b200 import _lib
+    n1, n2 = example_fit["n_corners"]
+    views = np.ascontiguousarray([list(r) + list(t) for r, t in example_fit["view_list"]], dtype=np.float64)
+    obj = np.ascontiguousarray(example_fit["obj_np"], dtype=np.float64).reshape(-1, 3)
+    img = np.ascontiguousarray(example_fit["corners_np"], dtype=np.float64).reshape(6, -1, 2)
+    ir, ic = np.ascontiguousarray(samples[:, :, 0]), np.ascontiguousarray(samples[:, :, 1])
+    sums = np.zeros(4)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(_lib.lib.cc_calculate_errors_f64_host(_lib.context(0).handle, C.byref(c._intr), p(views), 6, p(obj), p(img),
+                                                     n1, n2, p(ir), p(ic), 100, p(sums)))
+    n = n1 * n2 * 6
+    assert abs(np.sqrt(sums[0] / n) - eps["reprojection"]) < 1e-12 and abs(np.sqrt(sums[1] / n) - eps["projection"]) < 1e-12
+    assert abs(np.sqrt(sums[2] / ((n1 - 1) * (n2 - 1)) / 6) - eps["distance"]) < 1e-12
 
 
 def test_save_load_round_trip(cc, tmp_path, example_fit):

@@ -310,3 +310,65 @@ def test_lm_fit_views_sharded_over_two_gpus(cc):
     assert d0["rms"] == r0["rms"]
     assert d0["collectives"] == 2 + 2 * d0["iterations"] or d0["collectives"] >= 2 + 2 * d0["iterations"]   # init + two per iteration
     assert np.allclose(d0["init_intr"], intr0, rtol=1e-6) and d0["init_intr"] == d1["init_intr"]
+
+
+def _group_worker(out):
+    """One PROCESS, two GPUs: cc_ctx_create_group + cc_reproj_jtj_f64 per device + one grouped all-reduce."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from cameracalibrations_b200 import _lib
+    lib = _lib.lib
+    devs = (C.c_int * 2)(0, 1)
+    ctxs = (C.c_void_p * 2)()
+    _lib.check(lib.cc_ctx_create_group(2, devs, ctxs))
+    nr, rk = C.c_int(), C.c_int()
+    sizes = []
+    for i in range(2):
+        _lib.check(lib.cc_comm_size(ctxs[i], C.byref(nr), C.byref(rk)))
+        sizes.append((nr.value, rk.value))
+    rng = np.random.default_rng(5)
+    nv, nc = 40, 280
+    views = np.concatenate([rng.normal(0, 0.3, (nv, 3)), np.array([-10.0, -7.0, 40.0]) + rng.normal(0, 2.0, (nv, 3))], 1)
+    obj = np.array([[a, b, 0.0] for b in range(14) for a in range(20)], dtype=np.float64)
+    img = rng.normal(1000.0, 300.0, (nv, nc, 2))
+    intr = _lib.make_intr(2800.0, 2800.0, 1080.0, 1920.0, -0.12, 1.0)
+    def run(ctx, dev, v, im):
+        with torch.cuda.device(dev):
+            tv = torch.from_numpy(v).to(f"cuda:{dev}"); to = torch.from_numpy(obj).to(f"cuda:{dev}"); ti = torch.from_numpy(im).to(f"cuda:{dev}")
+            pv = torch.empty((len(v), 66), dtype=torch.float64, device=f"cuda:{dev}")
+            sh = torch.empty(21, dtype=torch.float64, device=f"cuda:{dev}")
+            _lib.check(lib.cc_reproj_jtj_f64(ctx, C.byref(intr), 1.0, C.c_void_p(tv.data_ptr()), len(v), C.c_void_p(to.data_ptr()),
+                                             C.c_void_p(ti.data_ptr()), nc, C.c_void_p(pv.data_ptr()), C.c_void_p(sh.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            return sh, (tv, to, ti, pv)
+    whole, keep0 = run(ctxs[0], 0, views, img)
+    torch.cuda.synchronize(0)
+    whole = whole.cpu().numpy().copy()
+    a, keep1 = run(ctxs[0], 0, views[:25], img[:25])
+    b, keep2 = run(ctxs[1], 1, views[25:], img[25:])
+    bufs = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    streams = (C.c_void_p * 2)(torch.cuda.current_stream(0).cuda_stream, torch.cuda.current_stream(1).cuda_stream)
+    _lib.check(lib.cc_allreduce_shared_group(ctxs, 2, bufs, 21, streams))
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    out.put((sizes, whole, a.cpu().numpy(), b.cpu().numpy()))
+    _lib.check(lib.cc_ctx_destroy_group(2, ctxs))
+
+
+@pytest.mark.gpu
+def test_single_process_group_of_two_gpus(cc):
+    """SURVEY 8b's multi-device context: one process, cc_ctx_create_group over two devices, the 21-double block of
+    each device's views summed by one grouped NCCL call == the block of all views on one device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    p = ctx.Process(target=_group_worker, args=(out,))     # own process: NCCL state does not leak into the suite
+    p.start()
+    sizes, whole, a, b = out.get(timeout=300)
+    p.join(timeout=120)
+    assert p.exitcode == 0
+    assert sizes == [(2, 0), (2, 1)]
+    assert np.array_equal(a, b)                             # every rank holds the same sum
+    np.testing.assert_allclose(a, whole, rtol=1e-12)
