@@ -279,6 +279,7 @@ int cc_ctx_destroy(cc_ctx* ctx) {
         if (ctx->pipe_out[k]) cudaFree(ctx->pipe_out[k]);
     }
     if (ctx->jtj_scratch) cudaFree(ctx->jtj_scratch);
+    if (ctx->scratch_event) cudaEventDestroy(ctx->scratch_event);
     lm_free_workspace(ctx);
     comm_free(ctx);
     rectify_free_plans(ctx);

@@ -29,6 +29,8 @@ void narrow_chain(const ChainD& d, ChainF* f);
 void rectify_free_plans(struct ::cc_ctx* ctx);
 void rectify_free_sched(struct ::cc_ctx* ctx);
 void ingest_free(struct ::cc_ctx* ctx);
+int scratch_acquire(struct ::cc_ctx* ctx, size_t elems, cudaStream_t st);
+int scratch_release(struct ::cc_ctx* ctx, cudaStream_t st);
 int jpeg_info(const uint8_t* data, size_t length, int* sz1, int* sz2, int* channels);
 int jpeg_decode_u8c3(struct ::cc_ctx* ctx, const uint8_t* const* jpegs, const size_t* lengths, int n, uint8_t* dst,
                      int sz1, int sz2, size_t pitch, size_t frame_stride, cudaStream_t st);
@@ -49,6 +51,11 @@ struct cc_ctx {
     // reprojection scratch: [21][nviews] component-major partials
     double* jtj_scratch;
     size_t jtj_scratch_elems;
+    // the scratch is shared by reproj_jtj / calc_errors / lm_*: calls on DIFFERENT streams are ordered
+    // through an event recorded on the previous user's stream (scratch_acquire)
+    cudaStream_t scratch_stream;
+    cudaEvent_t scratch_event;
+    int scratch_used;
     // host pipeline: NSLOT streams with device staging buffers
     static const int NSLOT = 4;
     cudaStream_t pipe_stream[NSLOT];

@@ -307,19 +307,11 @@ __global__ void lm_decide_kernel(LmState* __restrict__ st, const double* __restr
     if (st->iterations >= max_iter) st->done = 1;
 }
 
-static int ensure_lm_scratch(cc_ctx* ctx, size_t elems) {
-    if (ctx->jtj_scratch_elems >= elems) return CC_OK;
-    if (ctx->jtj_scratch) { CC_CUDA(cudaFree(ctx->jtj_scratch)); ctx->jtj_scratch = nullptr; }
-    ctx->jtj_scratch_elems = 0;
-    CC_CUDA(cudaMalloc(&ctx->jtj_scratch, elems * sizeof(double)));
-    ctx->jtj_scratch_elems = elems;
-    return CC_OK;
-}
 
 int launch_lm_schur(cc_ctx* ctx, const double* per_view, int nviews, double lambda, double* yz,
                     double* schur, cudaStream_t st) {
     const int nv = nviews > 0 ? nviews : 1;
-    int rc = ensure_lm_scratch(ctx, (size_t)kSchurComponents * nv);
+    int rc = scratch_acquire(ctx, (size_t)kSchurComponents * nv, st);
     if (rc) return rc;
     if (nviews > 0) {
         lm_schur_kernel<<<(nviews + kLmThreads - 1) / kLmThreads, kLmThreads, 0, st>>>(per_view, nviews, lambda, yz,
@@ -330,6 +322,7 @@ int launch_lm_schur(cc_ctx* ctx, const double* per_view, int nviews, double lamb
     lm_reduce_kernel<<<kSchurComponents, 256, 0, st>>>(ctx->jtj_scratch, nviews, schur);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
+    if ((rc = scratch_release(ctx, st))) return rc;
     return CC_OK;
 }
 
@@ -337,7 +330,7 @@ int launch_lm_update(cc_ctx* ctx, const double* shared, const double* schur, dou
                      unsigned free_mask, const double* yz, const cc_view* views_in, int nviews,
                      cc_view* views_out, double* delta, cudaStream_t st) {
     const int nv = nviews > 0 ? nviews : 1;
-    int rc = ensure_lm_scratch(ctx, (size_t)kSchurComponents * nv);
+    int rc = scratch_acquire(ctx, (size_t)kSchurComponents * nv, st);
     if (rc) return rc;
     // at least one block: block 0 publishes the shared-parameter step even without local views
     const int blocks = std::max(1, (nviews + kLmThreads - 1) / kLmThreads);
@@ -348,6 +341,7 @@ int launch_lm_update(cc_ctx* ctx, const double* shared, const double* schur, dou
     lm_reduce_kernel<<<2, 256, 0, st>>>(ctx->jtj_scratch, nviews, delta + 4);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
+    if ((rc = scratch_release(ctx, st))) return rc;
     return CC_OK;
 }
 
@@ -430,7 +424,7 @@ int lm_fit_device(cc_ctx* ctx, cc_intr* intr, double aspect, unsigned free_mask,
     int rc = lm_workspace(ctx, nviews, &w);
     if (rc) return rc;
     const int nv1 = nviews > 0 ? nviews : 1;
-    if ((rc = ensure_lm_scratch(ctx, (size_t)kSchurComponents * nv1))) return rc;
+    if ((rc = scratch_acquire(ctx, (size_t)kSchurComponents * nv1, st))) return rc;
     double* schur = w->small;
     double* red = w->small + 24;
     double* sh_cur = w->small + 48;
@@ -484,6 +478,7 @@ int lm_fit_device(cc_ctx* ctx, cc_intr* intr, double aspect, unsigned free_mask,
         CC_CUDA(cudaMemcpyAsync(&w->host_state[slot], w->state, sizeof(LmState), cudaMemcpyDeviceToHost, st));
         CC_CUDA(cudaEventRecord(w->ev[slot], st));
     }
+    if ((rc = scratch_release(ctx, st))) return rc;
     // the one wait of the call: the caller gets the intrinsics back on the host
     LmState fin;
     CC_CUDA(cudaMemcpyAsync(&w->host_state[0], w->state, sizeof(LmState), cudaMemcpyDeviceToHost, st));

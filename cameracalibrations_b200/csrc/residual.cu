@@ -410,7 +410,13 @@ calc_errors_kernel(const cc_intr intr, const cc_view* __restrict__ views, int nv
     }
 }
 
-static int ensure_scratch(cc_ctx* ctx, size_t elems) {
+// The per-context scratch ([components][views] partials) is shared by reproj_jtj, calc_errors and the
+// LM kernels.  Every launcher brackets its use: scratch_acquire grows the buffer and, when the call
+// comes on a stream other than the previous user's, makes it wait for the event that user recorded
+// in scratch_release -- two streams of one context can never race on the buffer.
+int scratch_acquire(cc_ctx* ctx, size_t elems, cudaStream_t st) {
+    if (ctx->scratch_used && ctx->scratch_stream != st && ctx->scratch_event)
+        CC_CUDA(cudaStreamWaitEvent(st, ctx->scratch_event, 0));
     if (ctx->jtj_scratch_elems >= elems) return CC_OK;
     if (ctx->jtj_scratch) { CC_CUDA(cudaFree(ctx->jtj_scratch)); ctx->jtj_scratch = nullptr; }
     ctx->jtj_scratch_elems = 0;
@@ -418,12 +424,19 @@ static int ensure_scratch(cc_ctx* ctx, size_t elems) {
     ctx->jtj_scratch_elems = elems;
     return CC_OK;
 }
+int scratch_release(cc_ctx* ctx, cudaStream_t st) {
+    if (!ctx->scratch_event) CC_CUDA(cudaEventCreateWithFlags(&ctx->scratch_event, cudaEventDisableTiming));
+    CC_CUDA(cudaEventRecord(ctx->scratch_event, st));
+    ctx->scratch_stream = st;
+    ctx->scratch_used = 1;
+    return CC_OK;
+}
 
 int launch_reproj_jtj(cc_ctx* ctx, const cc_intr* intr, double aspect, const cc_view* views,
                       int nviews, const double* obj, const double* img, int ncorners,
                       double* per_view, double* shared, cudaStream_t st) {
     CC_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15u) == 0, "img must be 16-byte aligned");
-    int rc = ensure_scratch(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1));
+    int rc = scratch_acquire(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1), st);
     if (rc) return rc;
     if (nviews > 0) {
         SharedIntr in{intr->frow, intr->fcol, intr->crow, intr->ccol, intr->k, aspect,
@@ -436,13 +449,14 @@ int launch_reproj_jtj(cc_ctx* ctx, const cc_intr* intr, double aspect, const cc_
     reduce_components_kernel<<<CC_SHARED, 256, 0, st>>>(ctx->jtj_scratch, nviews, shared);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
+    if ((rc = scratch_release(ctx, st))) return rc;
     return CC_OK;
 }
 
 int launch_reproj_jtj_state(cc_ctx* ctx, const LmState* st, int which, const LmBufs& b, double aspect,
                             double checker_size, int nviews, const double* obj, const double* img,
                             int ncorners, double* shared_out, cudaStream_t stream) {
-    int rc = ensure_scratch(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1));
+    int rc = scratch_acquire(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1), stream);
     if (rc) return rc;
     if (nviews > 0) {
         reproj_jtj_state_kernel<<<(nviews + kResWarps - 1) / kResWarps, kResThreads, 0, stream>>>(
@@ -453,6 +467,7 @@ int launch_reproj_jtj_state(cc_ctx* ctx, const LmState* st, int which, const LmB
     reduce_components_state_kernel<<<CC_SHARED, 256, 0, stream>>>(st, ctx->jtj_scratch, nviews, shared_out);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
+    if ((rc = scratch_release(ctx, stream))) return rc;
     return CC_OK;
 }
 
@@ -462,7 +477,7 @@ int launch_calc_errors(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, i
     CC_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15u) == 0, "img must be 16-byte aligned");
     const size_t smem = (size_t)kResWarps * n1 * n2 * 3 * sizeof(double);
     CC_REQUIRE(smem <= 200 * 1024, "too many corners per view for the fused kernel");
-    int rc = ensure_scratch(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1));
+    int rc = scratch_acquire(ctx, (size_t)CC_SHARED * (size_t)(nviews > 0 ? nviews : 1), st);
     if (rc) return rc;
     if (nviews > 0) {
         if (smem > 48 * 1024)
@@ -477,6 +492,7 @@ int launch_calc_errors(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, i
     reduce_components_kernel<<<4, 256, 0, st>>>(ctx->jtj_scratch, nviews, sums);
     ctx->launches++;
     CC_CUDA(cudaGetLastError());
+    if ((rc = scratch_release(ctx, st))) return rc;
     return CC_OK;
 }
 

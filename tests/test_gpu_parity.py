@@ -783,3 +783,26 @@ def test_jpeg_ingest_feeds_the_plot_loop(cc, example_fit):
         cc.load_jpegs([enc[0], cv2.imencode(".jpg", imgs[0][:100])[1].tobytes()])
     with pytest.raises(cc.CamcalError):
         cc.jpeg_info(b"not a jpeg at all, just bytes")
+
+
+def test_reproj_on_two_streams_of_one_context(cc):
+    """The per-context scratch of reproj_jtj / calc_errors / LM is ordered across streams:
+    the same call issued alternately on two streams gives the same block every time."""
+    rng = np.random.default_rng(8)
+    nv, nc = 3000, 280
+    views = np.concatenate([rng.normal(0, 0.3, (nv, 3)), np.array([-10.0, -7.0, 40.0]) + rng.normal(0, 2.0, (nv, 3))], 1)
+    obj = np.array([[a, b, 0.0] for b in range(14) for a in range(20)], dtype=np.float64)
+    img = rng.normal(1000.0, 300.0, (nv, nc, 2))
+    tv, to, ti = _dev(views), _dev(obj), _dev(img)
+    tv2, ti2 = _dev(views[::-1].copy()), _dev(img[::-1].copy())
+    ref = cc.reproj_jtj(C3_INTR, 1.0, tv, to, ti)[1].cpu().numpy()
+    ref2 = cc.reproj_jtj(C3_INTR, 1.0, tv2, to, ti2)[1].cpu().numpy()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(12):
+        with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+            outs.append(cc.reproj_jtj(C3_INTR, 1.0, tv if i % 2 == 0 else tv2, to, ti if i % 2 == 0 else ti2)[1])
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert np.array_equal(o.cpu().numpy(), ref if i % 2 == 0 else ref2), i
