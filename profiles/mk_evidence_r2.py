@@ -1,7 +1,7 @@
 """Round-2 evidence: turn the raw GPU outputs (gpurun_out/, scratch) into the committed files under profiles/r2/.
     python profiles/mk_evidence_r2.py
 inputs  gpurun_out/r2_bench.json, r2_bench_ref.json   plain `python bench.py` / `--impl reference` runs (no profiler)
-        gpurun_out/r2_launches.csv                    ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu
+        gpurun_out/r2_launches.csv                    ncu --metrics gpu__time_duration.sum --clock-control none -c 4000  python bench.py --steps 2 --warmup 3 --no-cpu
         gpurun_out/r2_all.ncu-rep                     ncu --set full --import-source on --clock-control none  python profiles/prof_kernels.py all --reps 1
 outputs profiles/r2/bench.json, bench_ref.json, launches.csv, launches_summary.txt, ncu_full_summary.txt,
         ncu_hot_<kernel>.txt (executed-instruction mix + stall reasons of the hot kernels), sass_<kernel>.txt (static
@@ -63,7 +63,7 @@ if os.path.exists(src):
         a[0] += 1; a[1] += us
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(out, "launches_summary.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 600  python bench.py --steps 2 --warmup 3 --no-cpu\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 4000  python bench.py --steps 2 --warmup 3 --no-cpu\n")
         f.write("# whole process (warm-up, timed steps, e2e leg, extras); per-launch times are cold-cache and serialised:\n")
         f.write("# the SHARE column is what must agree with bench.py, not the absolute times\n")
         f.write(f"# {'launches':>8s} {'mean us':>10s} {'share':>7s}  kernel\n")
