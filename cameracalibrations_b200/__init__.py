@@ -17,6 +17,7 @@ _LAZY = {
     "calibration": ("Calibration", "rectification", "get_ratio", "get_axes", "image_transformations", "warp",
                     "warp_views", "rectify_map", "load_jpegs", "jpeg_info", "reproj_jtj", "calculate_errors", "allreduce_shared", "save", "load", "views_tensor"),
     "fit": ("fit", "detect_fit", "fit_model"),
+    "plotting": ("plot",),
     "lm": ("lm_fit", "lm_fit_host", "lm_fit_device", "initial_guess", "initial_guess_device"),
 }
 _WHERE = {name: mod for mod, names in _LAZY.items() for name in names}
@@ -37,4 +38,4 @@ __all__ = ["Calibration", "rectification", "fit", "detect_fit", "get_ratio", "ge
            "image_transformations", "warp", "warp_views", "rectify_map", "load_jpegs", "jpeg_info", "reproj_jtj", "calculate_errors", "save",
            "load", "views_tensor", "shard_range", "shard_frames", "CamcalError", "Context", "context",
            "device_count", "RowCol", "XYZ", "lm_fit", "lm_fit_host", "lm_fit_device", "initial_guess",
-           "initial_guess_device", "allreduce_shared", "fit_model"]
+           "initial_guess_device", "allreduce_shared", "fit_model", "plot"]

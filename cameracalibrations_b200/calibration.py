@@ -326,7 +326,7 @@ def load_jpegs(datas, device=None, out=None):
     u8c3 frame layout that warp() / warp_views() take."""
     blobs = []
     for d in datas:
-        if isinstance(d, (str, bytes.__class__)) and not isinstance(d, (bytes, bytearray, memoryview)):
+        if isinstance(d, str):                       # a file name
             with open(d, "rb") as f:
                 d = f.read()
         blobs.append(bytes(d))

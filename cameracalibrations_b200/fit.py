@@ -84,9 +84,6 @@ def detect_fit(files, n_corners, with_distortion=True, aspect=1, solver="opencv"
 def fit(files, n_corners, checker_size, aspect=1, with_distortion=True, inverse_samples=100,
         with_plot=False, rng=None, solver="opencv"):
     """Returns the tuple (c, eps) like the reference."""
-    if with_plot:                                # before any work is done
-        raise NotImplementedError("debug PNG output (src/plot_calibration.jl:24-44) is out of scope; "
-                                  "use image_transformations(c, i, detect_fit(...)['imgpointss'], ...) + warp()")
     files = list(dict.fromkeys(files))           # unique(files)
     d = detect_fit(files, n_corners, with_distortion, aspect, solver=solver)
     objpoints = d["objpoints"] * checker_size
@@ -94,4 +91,7 @@ def fit(files, n_corners, checker_size, aspect=1, with_distortion=True, inverse_
                              checker_size, d["k"], d["files"])
     eps = calculate_errors(c, d["imgpointss"], objpoints, checker_size, d["sz"], d["files"], n_corners,
                            inverse_samples, rng=rng)
+    if with_plot:                                # src/buildcalibrations.jl:22: plot(c, imgpointss, n_corners, checker_size, sz)
+        from .plotting import plot
+        plot(c, d["imgpointss"], n_corners, checker_size, d["sz"])
     return c, eps

@@ -4,6 +4,7 @@ seeded inputs.  Tolerances (BASELINE.json north_star):
   FP32 fast path          <= 1e-3 px (round trip / map error)
   FP64 remap              bit-exact map, indices, weights and output
 """
+import os
 import ctypes as C
 
 import numpy as np
@@ -806,3 +807,36 @@ def test_reproj_on_two_streams_of_one_context(cc):
     torch.cuda.synchronize()
     for i, o in enumerate(outs):
         assert np.array_equal(o.cpu().numpy(), ref if i % 2 == 0 else ref2), i
+
+
+def test_plot_writes_the_rectified_images(cc, example_fit, tmp_path):
+    """plot(c, imgpointss, n_corners, checker_size, sz), src/plot_calibration.jl:36-44: every image rectified with
+    its own extrinsic in one views call; the files on disk are the oracle's rectification of the red-cross images
+    except where the blue crosses were drawn."""
+    cv2 = pytest.importorskip("cv2")
+    from cameracalibrations_b200.plotting import _draw_crosses, RED
+    n1, n2 = example_fit["n_corners"]
+    sz = (376, 500)                                     # rows, cols (376: word-aligned u8 lines)
+    rng = np.random.default_rng(31)
+    files, imgs = [], []
+    for i in range(6):
+        img = rng.integers(0, 256, (sz[0], sz[1], 3), dtype=np.uint8)      # (rows, cols, RGB)
+        f = str(tmp_path / f"{i + 1}.png")
+        cv2.imwrite(f, img[:, :, ::-1])
+        files.append(f); imgs.append(img)
+    c = _calib(cc, example_fit["intr_tuple"], example_fit["view_list"], files)
+    ips = np.asarray(example_fit["corners_np"], dtype=np.float64).reshape(6, -1, 2)
+    out = cc.plot(c, ips, (n1, n2), 1.0, sz, dir=str(tmp_path / "debug"))
+    assert [os.path.basename(p) for p in out] == [f"{i + 1}.png" for i in range(6)]
+    for i, p in enumerate(out):
+        got = cv2.imread(p, cv2.IMREAD_COLOR)[:, :, ::-1]                   # (rows, cols, RGB)
+        assert got.shape == (sz[0], sz[1], 3)
+        frame = np.ascontiguousarray(imgs[i].transpose(1, 0, 2))            # frame layout [c][r]
+        _draw_crosses(frame, ips[i], n1, RED)
+        ratio, axs = cc.image_transformations(c, i, ips, 1.0, (n1, n2), sz)
+        ch = oc.chain(example_fit["intr_tuple"], *example_fit["view_list"][i])
+        ref = oc.rectify_u8c3(ch, 1.0 / ratio, axs, frame[None], fill=(0, 0, 0))[0].transpose(1, 0, 2)
+        diff = np.any(got != ref, axis=-1)
+        assert diff.mean() < 0.03                                           # only the blue crosses differ
+        assert np.all(got[diff] == np.array([0, 0, 255], dtype=np.uint8))
+        assert diff.sum() > 0                                               # and they were drawn
