@@ -99,3 +99,36 @@ def test_view_index_semantics(cc):
     with pytest.raises(ValueError):
         c._index("missing.png")
     assert c.checker_size == 1.0
+
+
+def test_ingest_and_group_entry_points_fail_loudly_without_a_device(cc):
+    """No CPU decode path, no silent success: without a CUDA device the JPEG ingest and the multi-device
+    context return status codes; bad arguments are rejected before anything else."""
+    import torch
+    from cameracalibrations_b200 import _lib
+    assert _lib.lib.cc_jpeg_info(None, 0, None, None, None) == -1
+    assert _lib.lib.cc_jpeg_decode_u8c3(None, None, None, 1, None, 4, 4, 4, 16, None) == -1
+    assert _lib.lib.cc_ctx_create_group(0, None, None) == -1
+    assert _lib.lib.cc_allreduce_shared_group(None, 0, None, 0, None) == -1
+    if torch.cuda.is_available():
+        return
+    with pytest.raises(cc.CamcalError):
+        cc.jpeg_info(b"\xff\xd8\xff\xe0 definitely not a complete jpeg")
+    devs = (C.c_int * 1)(0)
+    ctxs = (C.c_void_p * 1)()
+    assert _lib.lib.cc_ctx_create_group(1, devs, ctxs) == -2 and not ctxs[0]      # CC_ERR_NO_DEVICE
+
+
+def test_draw_crosses_is_the_reference_rule():
+    """draw_crosses!, src/plot_calibration.jl:24-28: radius = round(|ij[1] - ij[n1]| / n1 / 5), a horizontal and a
+    vertical bar of +-radius through every rounded corner, clipped at the frame."""
+    from cameracalibrations_b200.plotting import _draw_crosses
+    frame = np.zeros((40, 60, 3), dtype=np.uint8)              # frame layout [c][r]: sz1 = 60 rows, sz2 = 40 columns
+    pts = np.array([[10.2, 5.4], [30.0, 5.0], [50.4, 5.0], [59.6, 39.7]])     # (row, col), 1-based; n1 = 3
+    _draw_crosses(frame, pts, 3, (255, 0, 0))
+    radius = int(np.rint(np.hypot(10 - 50, 0) / 3 / 5))        # = 3
+    assert radius == 3
+    assert np.all(frame[4, 9 - 3:9 + 4, 0] == 255) and frame[4, 9 - 4, 0] == 0 and frame[4, 9 + 4, 0] == 0    # along the rows
+    assert np.all(frame[4 - 3:4 + 4, 9, 0] == 255) and frame[4 + 4, 9, 0] == 0                               # along the columns
+    assert np.all(frame[39, 56:60, 0] == 255) and np.all(frame[36:40, 59, 0] == 255)                          # clipped at the corner
+    assert frame[..., 1].max() == 0 and frame[..., 2].max() == 0
