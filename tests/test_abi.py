@@ -132,3 +132,26 @@ def test_draw_crosses_is_the_reference_rule():
     assert np.all(frame[4 - 3:4 + 4, 9, 0] == 255) and frame[4 + 4, 9, 0] == 0                               # along the columns
     assert np.all(frame[39, 56:60, 0] == 255) and np.all(frame[36:40, 59, 0] == 255)                          # clipped at the corner
     assert frame[..., 1].max() == 0 and frame[..., 2].max() == 0
+
+
+def _build_c_consumer(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "cameracalibrations_b200")
+    exe = str(tmp_path / "abi_consumer")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", libdir, "-lcamcal_b200", "-lm",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr                    # the header is valid strict C99 and every symbol links
+    return subprocess.run([exe], capture_output=True, text=True)
+
+
+def test_plain_c_consumer_of_the_abi(tmp_path):
+    """include/camcal_b200.h + the .so from C, no Python or torch in between: the host helpers work, and a box
+    without a GPU gets CC_ERR_NO_DEVICE (printed as 'no device'), never a CPU result."""
+    import torch
+    r = _build_c_consumer(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip() == ("ok" if torch.cuda.is_available() else "no device")

@@ -875,3 +875,10 @@ def test_rectify_random_geometries_bit_exact(cc, seed):
     both = np.any(ref8 != np.array((3, 2, 1), np.uint8), -1) & np.any(fast8 != np.array((3, 2, 1), np.uint8), -1)
     if both.any():
         assert np.abs(fast8[both].astype(np.int16) - ref8[both].astype(np.int16)).max() <= 2
+
+
+def test_plain_c_consumer_computes_on_the_gpu(cc, tmp_path):
+    """tests/c/abi_consumer.c: world->pixel->world, a rectification and the error codes through the C ABI from C."""
+    from test_abi import _build_c_consumer
+    r = _build_c_consumer(tmp_path)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
