@@ -40,7 +40,19 @@ constexpr int kTLf = CAMCAL_TL_F32;    // f32c1: lines per tile (a warp owns kTL
 constexpr int kTLmax = 32;             // most lines of a tile (sizes the per-stage q2 slots)
 // most frames one unit rectifies with one map (measured, profiles/r1_rectify.md: the costlier the
 // map, the larger the group; the cheaper, the finer the units for the tail of the ticket queue)
-constexpr int kFGf32Exact = 12, kFGf32Fast = 4, kFGu8Exact = 16, kFGu8Fast = 12;
+#ifndef CAMCAL_FG_F32_EXACT
+#define CAMCAL_FG_F32_EXACT 12
+#endif
+#ifndef CAMCAL_FG_F32_FAST
+#define CAMCAL_FG_F32_FAST 4
+#endif
+#ifndef CAMCAL_FG_U8_EXACT
+#define CAMCAL_FG_U8_EXACT 16
+#endif
+#ifndef CAMCAL_FG_U8_FAST
+#define CAMCAL_FG_U8_FAST 12
+#endif
+constexpr int kFGf32Exact = CAMCAL_FG_F32_EXACT, kFGf32Fast = CAMCAL_FG_F32_FAST, kFGu8Exact = CAMCAL_FG_U8_EXACT, kFGu8Fast = CAMCAL_FG_U8_FAST;
 #ifndef CAMCAL_TL_U8
 #define CAMCAL_TL_U8 32
 #endif
@@ -76,7 +88,7 @@ constexpr int kProducerSleep = CAMCAL_PRODUCER_SLEEP;   // ns between the produc
 #define CAMCAL_MINB 1
 #endif
 #ifndef CAMCAL_MINB_EXACT
-#define CAMCAL_MINB_EXACT 3
+#define CAMCAL_MINB_EXACT 4
 #endif
 // __launch_bounds__ min CTAs/SM of the staged f32c1 kernels (fast / exact coordinates)
 constexpr int kMinBlocks = CAMCAL_MINB, kMinBlocksExact = CAMCAL_MINB_EXACT;
@@ -99,6 +111,8 @@ struct TileCfg {
     int strips;            // tiles along the first axis
     uint32_t units;        // strips * ntiles2 * frame groups
     int fg;                // frames per group: the tile's map is built once per group and reused
+    uint32_t widen_mul;    // f32c1 exact: 2^29, the multiplier of the integer float->double widening (a kernel
+                           // parameter so that ptxas keeps ONE IMAD.WIDE instead of two shifts, rectify_f32c1.cuh)
 };
 
 // f32c1: per-tile header precomputed on the host (RectPlan), read straight from global memory
@@ -633,6 +647,7 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     int rc = CC_OK;
     if (tma) {
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
+        cfg.widen_mul = 0x20000000u;
         const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, 0, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)

@@ -59,6 +59,11 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
     return v;
 }
 
+#ifndef CAMCAL_F32_BORDER
+#define CAMCAL_F32_BORDER 1
+#endif
+constexpr bool kBorderUnrolled = CAMCAL_F32_BORDER != 0;
+
 // ---- direct kernel: no staging (unaligned layouts, footprints too large for a box) -------
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads)
@@ -103,6 +108,38 @@ rectify_f32c1_direct_kernel(const __grid_constant__ RectExact pe, const __grid_c
 #endif
 constexpr bool kKeepE = CAMCAL_F32_KEEP_E != 0;
 
+// Widening the four taps float -> double is what bounds the exact kernel: F2F.F64.F32 runs on the
+// XU pipe (4 lanes per clock and sub-partition; ncu: 75 % busy, profiles/r2).  For a finite float
+// f >= +0 with bit pattern b, the 64-bit integer b * 2^29 read as a double is f * 2^-896 EXACTLY
+// (exponent field e instead of e + 896; zero stays zero; a float denormal becomes the double
+// denormal with the same significand) -- one IMAD.WIDE.U32 on the idle FMA pipe.  The scale is
+// undone for free: the map keeps d2 * 2^896 instead of d2, so e2' = 2^896 - d2' and the two inner
+// products e2'*a', d2'*a' are the unscaled products rounded once -- bit for bit the oracle's
+// blend (rounding commutes with a power-of-two scale; nothing under- or overflows: e2*a >= 2^-202).
+// Negative, -0, Inf and NaN taps do not fit the rule: the unsigned maximum of a warp's tap bits
+// tells (>= 0x7f800000), and such a warp takes the F2F blend for that frame.
+#ifndef CAMCAL_F32_WIDEN
+#define CAMCAL_F32_WIDEN 0
+#endif
+constexpr bool kWiden = CAMCAL_F32_WIDEN != 0;
+constexpr double kWidenScale = 0x1p896, kWidenUnscale = 0x1p-896;
+
+__device__ __forceinline__ double widen_scaled(float a, uint32_t mul) {
+    unsigned long long r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(__float_as_uint(a)), "r"(mul));
+    return __longlong_as_double((long long)r);
+}
+__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
+
+// bilerp() on taps scaled by 2^-896 with the second-axis weight scaled by 2^896
+__device__ __forceinline__ double bilerp_scaled(double a00, double a10, double a01, double a11, double d1,
+                                                double d2s) {
+    const double e1 = 1.0 - d1, e2s = kWidenScale - d2s;
+    const double lo = fma(d2s, a01, e2s * a00);
+    const double hi = fma(d2s, a11, e2s * a10);
+    return fma(d1, hi, e1 * lo);
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
@@ -141,10 +178,21 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
     int s = 0;
     uint32_t phase = 0;
+    int4 pos = make_int4(0, 0, 0, 0);
+    int frames_left = 0;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
-        const int4 pos = ring.pos[s];
-        if (pos.z < 0) break;
+        // the slot is read on a unit's first frame only; the frames of the unit are counted down in
+        // (warp-uniform) registers -- no LDS + two dependent branches in front of every frame
+        if (kPosTrack ? frames_left == 0 : true) {
+            pos = ring.pos[s];
+            if (pos.z < 0) break;
+            frames_left = kPosTrack ? pos.w : 0;
+        } else {
+            pos.z += 1;
+            pos.w = 0;
+        }
+        if (kPosTrack) --frames_left;
         if (pos.w) {                                   // ---- first frame of a unit: build the map
             const TileHdr* h = &ring.hdr[s];
             const int a_w = pos.x * kT;
@@ -172,6 +220,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                     floor_index<kFloorMode1>(row, Mk1, t1, h1, wd1[e]);
                     floor_index<kFloorMode2>(col, Mk2, t2, h2, wd2[e]);
                     if (kKeepE) { we1[e] = 1.0 - wd1[e]; we2[e] = 1.0 - wd2[e]; }
+                    if (kWiden) wd2[e] *= kWidenScale;     // exact
                     const bool st = (((h1 ^ 0x43300000u) | (h2 ^ 0x43300000u)) == 0u) & (t1 < R1) & (t2 < R2);
                     rel[e] = rel0 + t2 * box_pitch_b + t1 * 4u;
                     if (st) m_staged |= 1u << e;
@@ -216,6 +265,75 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         float* o = dst + (long long)pos.z * g.frame_stride + off0;
         const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
         const uint32_t sbase1 = sbase + box_pitch_b;    // one uniform base per source line: LDS [R + UR + imm], no per-pixel add
+        auto border = [&](float* o) {
+            // border tiles (and frames whose taps the integer widening cannot take): per-pixel class.
+            // CAMCAL_F32_BORDER 1: staged and fill pixels unrolled (static indices into the map), then
+            // one rolled pass over what is left for the generic sampler (it needs no map entry);
+            // 0: round 1's rolled loop that selects the map entry through a compare chain -- 98
+            // instructions per pixel, 9 % of all executed instructions of c2 (profiles/r2_rectify.md)
+            if (kBorderUnrolled) {
+                float* ob = o;
+#pragma unroll
+                for (int e = 0; e < LPW; ++e, ob += pitch) {
+                    const uint32_t bit = 1u << e;
+                    if (m_skip & bit) continue;              // the output pixel itself is outside the frame
+                    if (m_staged & bit) {
+                        const uint32_t q = sbase + rel[e], q1 = sbase1 + rel[e];
+                        const float t00 = lds_f32(q), t10 = lds_f32_off<4>(q), t01 = lds_f32(q1), t11 = lds_f32_off<4>(q1);
+                        float v;
+                        if (EXACT) v = (float)bilerp((double)t00, (double)t10, (double)t01, (double)t11, wd1[e],
+                                                     kWiden ? wd2[e] * kWidenUnscale : wd2[e]);
+                        else v = bilerp_fast(t00, t10, t01, t11, (e & 1) ? wf1[e / 2].y : wf1[e / 2].x,
+                                             (e & 1) ? wf2[e / 2].y : wf2[e / 2].x);
+                        __stcs(ob, v);
+                    } else if (m_fill & bit) {
+                        __stcs(ob, fill);
+                    }
+                }
+                // what is left: x == n exactly, footprints that leave the box (needs no map entry: rolled)
+                const uint32_t m_gen = ~(m_staged | m_fill | m_skip) & ((1u << LPW) - 1u);
+                if (m_gen) {
+                    RowTermD rtd;
+                    RowTermF rtf;
+                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+#pragma unroll 1
+                    for (int e = 0; e < LPW; ++e)
+                        if ((m_gen >> e) & 1u)
+                            __stcs(o + (long long)e * pitch, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b0 + e, fill));
+                }
+            } else {
+#pragma unroll 1
+            for (int e = 0; e < LPW; ++e, o += pitch) {
+                if ((m_skip >> e) & 1u) continue;
+                float v;
+                if ((m_staged >> e) & 1u) {
+                    // (rel[], weights indexed dynamically would spill: select through a switch-free copy)
+                    uint32_t r = 0;
+                    [[maybe_unused]] double d1 = 0, d2 = 0;
+                    [[maybe_unused]] float f1 = 0, f2 = 0;
+#pragma unroll
+                    for (int j = 0; j < LPW; ++j)
+                        if (j == e) {
+                            r = rel[j];
+                            if (EXACT) { d1 = wd1[j]; d2 = kWiden ? wd2[j] * kWidenUnscale : wd2[j]; }
+                            else { f1 = (j & 1) ? wf1[j / 2].y : wf1[j / 2].x; f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x; }
+                        }
+                    const uint32_t q = sbase + r, q1 = q + box_pitch_b;
+                    const float t00 = lds_f32(q), t10 = lds_f32_off<4>(q), t01 = lds_f32(q1), t11 = lds_f32_off<4>(q1);
+                    v = EXACT ? (float)bilerp((double)t00, (double)t10, (double)t01, (double)t11, d1, d2)
+                              : bilerp_fast(t00, t10, t01, t11, f1, f2);
+                } else if ((m_fill >> e) & 1u) {
+                    v = fill;
+                } else {
+                    RowTermD rtd;
+                    RowTermF rtf;
+                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+                    v = sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b0 + e, fill);
+                }
+                __stcs(o, v);
+            }
+            }
+        };
         if (all_staged) {
             float a00[LPW], a10[LPW], a01[LPW], a11[LPW];
 #pragma unroll
@@ -228,7 +346,24 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                 a00[e] = lds_f32(q); a10[e] = lds_f32_off<4>(q);
                 a01[e] = lds_f32(q1); a11[e] = lds_f32_off<4>(q1);
             }
-            if (EXACT) {
+            if (EXACT && kWiden) {
+                // blend as if every tap fits the integer widening, keep the maximum of the tap bits on
+                // the side; a warp that saw a negative / Inf / NaN tap redoes the frame below (F2F blend)
+                const uint32_t mul = cfg.widen_mul;
+                uint32_t mx = 0;
+                float* ow = o;
+#pragma unroll
+                for (int e = 0; e < LPW; ++e) {
+                    if (CAMCAL_F32_WIDEN != 2) {       // 2: tuning build without the check (wrong for negative taps)
+                        mx = umax3(mx, __float_as_uint(a00[e]), __float_as_uint(a10[e]));
+                        mx = umax3(mx, __float_as_uint(a01[e]), __float_as_uint(a11[e]));
+                    }
+                    __stcs(ow, (float)bilerp_scaled(widen_scaled(a00[e], mul), widen_scaled(a10[e], mul),
+                                                    widen_scaled(a01[e], mul), widen_scaled(a11[e], mul), wd1[e], wd2[e]));
+                    ow += pitch;
+                }
+                if (__any_sync(0xffffffffu, mx >= 0x7f800000u)) border(o);
+            } else if (EXACT) {
 #pragma unroll
                 for (int e = 0; e < LPW; ++e) {
                     if (kKeepE) {
@@ -254,40 +389,10 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                 }
             }
         } else {
-            // border tiles: per-pixel class
-#pragma unroll 1
-            for (int e = 0; e < LPW; ++e, o += pitch) {
-                if ((m_skip >> e) & 1u) continue;
-                float v;
-                if ((m_staged >> e) & 1u) {
-                    // (rel[], weights indexed dynamically would spill: select through a switch-free copy)
-                    uint32_t r = 0;
-                    [[maybe_unused]] double d1 = 0, d2 = 0;
-                    [[maybe_unused]] float f1 = 0, f2 = 0;
-#pragma unroll
-                    for (int j = 0; j < LPW; ++j)
-                        if (j == e) {
-                            r = rel[j];
-                            if (EXACT) { d1 = wd1[j]; d2 = wd2[j]; }
-                            else { f1 = (j & 1) ? wf1[j / 2].y : wf1[j / 2].x; f2 = (j & 1) ? wf2[j / 2].y : wf2[j / 2].x; }
-                        }
-                    const uint32_t q = sbase + r, q1 = q + box_pitch_b;
-                    const float t00 = lds_f32(q), t10 = lds_f32_off<4>(q), t01 = lds_f32(q1), t11 = lds_f32_off<4>(q1);
-                    v = EXACT ? (float)bilerp((double)t00, (double)t10, (double)t01, (double)t11, d1, d2)
-                              : bilerp_fast(t00, t10, t01, t11, f1, f2);
-                } else if ((m_fill >> e) & 1u) {
-                    v = fill;
-                } else {
-                    RowTermD rtd;
-                    RowTermF rtf;
-                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
-                    v = sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b0 + e, fill);
-                }
-                __stcs(o, v);
-            }
+            border(o);
         }
         __syncwarp();
-        if (lane_id == 0) mbar_arrive(&ring.empty[s]);
+        if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }

@@ -37,6 +37,21 @@ __device__ __forceinline__ void producer_wait(uint64_t* bar, uint32_t parity) {
     else mbar_wait<kProducerSleep>(bar, parity);
 }
 
+// consumers: CAMCAL_POS_TRACK 1 counts the frames of a unit in registers instead of reading the
+// slot per frame (measured 1 % SLOWER on c2 exact: 0.2123 vs 0.2100 ms -- two more live registers
+// in a 96-register kernel; kept as a knob); CAMCAL_ELECT: the arriving lane chosen with ELECT
+// instead of a lane-id compare (no S2R per frame; neutral)
+#ifndef CAMCAL_POS_TRACK
+#define CAMCAL_POS_TRACK 0
+#endif
+#ifndef CAMCAL_ELECT
+#define CAMCAL_ELECT 1
+#endif
+constexpr bool kPosTrack = CAMCAL_POS_TRACK != 0, kElectArrive = CAMCAL_ELECT != 0;
+// L2 eviction hint of the staged boxes (tma.cuh): 0 none, 1 evict_last, 2 evict_first, 3 evict_normal
+#ifndef CAMCAL_TMA_L2
+#define CAMCAL_TMA_L2 0
+#endif
 __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
     uint32_t u = 0;
     if (lane_id == 0) u = atomicAdd(&sched->next, 1u);
@@ -45,14 +60,16 @@ __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
 
 // PXB: multiplier from TileHdr.x0 to the tensor-map coordinate (1: f32c1 texels, and u8c3 whose x0 already is a byte offset).
 // A unit is (strip x, tile y, frame group): the producer publishes one slot per FRAME of the
-// group -- pos = (x, y, frame, 1 on the first frame of a unit) -- so the consumers rebuild the
-// tile's map only when pos.w is set and otherwise just gather.
+// group -- pos = (x, y, frame, number of frames of the unit on its first frame, else 0) -- the
+// consumers read the slot on a unit's first frame only (CAMCAL_POS_TRACK) and count the frames down.
 template <bool EXACT, int TL, int PXB>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const RectGeom& g, const TileCfg& cfg,
                                               const TileHdr* __restrict__ plan,
                                               const double* __restrict__ q2tab, RectSched* sched,
                                               SmemRing* ring, uint8_t* stage_mem, int lane_id) {
     if (lane_id == 0) tma_prefetch_desc(tmap);
+    [[maybe_unused]] uint64_t policy = 0;
+    if (CAMCAL_TMA_L2 != 0) policy = l2_policy<CAMCAL_TMA_L2>();
     int s = 0;
     uint32_t phase = 1;                            // a fresh barrier passes a parity-1 wait
     uint32_t u_next = take_ticket(sched, lane_id);
@@ -84,11 +101,12 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const Rec
                     if (TL > 32) ring->q2[s][lane_id + 32] = q2b;
                 }
             }
-            if (lane_id == 12) ring->pos[s] = make_int4(x, y, f, f == f0 ? 1 : 0);
+            if (lane_id == 12) ring->pos[s] = make_int4(x, y, f, f == f0 ? f1 - f0 : 0);   // .w: frames of the unit, on its first frame
             __syncwarp();
             if (lane_id == 0) {
                 mbar_arrive_expect_tx(&ring->full[s], (uint32_t)cfg.box_bytes);
-                tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, tmap, &ring->full[s], x0 * PXB, y0, f);
+                if (CAMCAL_TMA_L2 != 0) tma_load_3d_hint(stage_mem + (size_t)s * cfg.box_bytes, tmap, &ring->full[s], x0 * PXB, y0, f, policy);
+                else tma_load_3d(stage_mem + (size_t)s * cfg.box_bytes, tmap, &ring->full[s], x0 * PXB, y0, f);
             }
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
         }

@@ -409,10 +409,21 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 
     int s = 0;
     uint32_t phase = 0;
+    int4 pos = make_int4(0, 0, 0, 0);
+    int frames_left = 0;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
-        const int4 pos = ring.pos[s];
-        if (pos.z < 0) break;
+        // the slot is read on a unit's first frame only; the frames of the unit are counted down in
+        // (warp-uniform) registers -- no LDS + two dependent branches in front of every frame
+        if (kPosTrack ? frames_left == 0 : true) {
+            pos = ring.pos[s];
+            if (pos.z < 0) break;
+            frames_left = kPosTrack ? pos.w : 0;
+        } else {
+            pos.z += 1;
+            pos.w = 0;
+        }
+        if (kPosTrack) --frames_left;
         if (pos.w) {                                   // ---- first frame of a unit: build the map
             const TileHdr* h = &ring.hdr[s];
             const int a_w = pos.x * kT;
@@ -586,7 +597,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
         }
         __syncwarp();
-        if (lane_id == 0) mbar_arrive(&ring.empty[s]);
+        if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }

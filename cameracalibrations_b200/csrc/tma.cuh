@@ -21,6 +21,13 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (ELECT: no S2R of the lane id, which the compiler otherwise
+// rematerialises per frame in the register-bound consumers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{ .reg .pred q; elect.sync _|q, 0xffffffff; selp.u32 %0, 1, 0, q; }" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                  :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -74,6 +81,25 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         " [%0], [%1, {%3, %4, %5}], [%2];"
         :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
            "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// the same with an L2 eviction-priority hint (createpolicy): the source lines of a staged box are
+// wanted again by the neighbouring tiles (halo) within microseconds, the output never is
+template <int POLICY>   // 1: evict_last, 2: evict_first, 3: evict_normal via an explicit policy
+__device__ __forceinline__ uint64_t l2_policy() {
+    uint64_t pol;
+    if (POLICY == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (POLICY == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+           "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

@@ -273,6 +273,47 @@ def test_rectify_f32c1_bit_exact(cc, sz):
     assert np.array_equal(got_h, ref_h)
 
 
+@pytest.mark.parametrize("kind", ["tiny", "zeros", "negative", "neg_zero", "inf", "nan", "mixed"])
+def test_rectify_f32c1_exact_widening_special_values(cc, kind):
+    """The exact kernel widens float taps with an integer multiply (bits * 2^29 read as a double is the
+    value * 2^-896, rectify_f32c1.cuh) where every tap of a warp is finite and >= +0, and with F2F
+    elsewhere.  Both must be the oracle's FP64 blend bit for bit: denormals, zeros, the smallest and
+    largest normals on the integer path; negative values, -0, Inf and NaN on the other, per warp."""
+    sz = (640, 360)
+    intr = camera_for(sz)
+    ch, ip, ratio, axs = _rect_case(intr, sz)
+    c = _calib(cc, intr, [SYN_VIEW])
+    rng = np.random.default_rng(77)
+    frames = rng.random((3, sz[1], sz[0]), dtype=np.float32)
+    bits = frames.view(np.uint32)
+    pick = lambda p: rng.random(frames.shape) < p
+    if kind == "tiny":            # denormals, the smallest normals, values far below 2^-100, FLT_MAX
+        m = pick(0.5)
+        bits[m] = rng.integers(0, 0x02000000, size=int(m.sum()), dtype=np.uint32)
+        bits[pick(0.01)] = 0x7f7fffff
+        bits[pick(0.01)] = 1
+    elif kind == "zeros":
+        frames[pick(0.7)] = 0.0
+    elif kind == "negative":      # a negative tap anywhere in a warp's footprint sends that warp to F2F
+        frames[0] -= 0.5
+        frames[1][pick(1e-4)[1]] = -1.0
+    elif kind == "neg_zero":
+        bits[pick(0.3)] = 0x80000000
+    elif kind == "inf":
+        frames[pick(2e-4)] = np.inf
+    elif kind == "nan":
+        frames[pick(2e-4)] = np.nan
+    else:
+        bits[...] = rng.integers(0, 2 ** 32, size=frames.shape, dtype=np.uint32)
+        bits[0] &= 0x7fffffff     # frame 0 non-negative, a few Inf/NaN by chance
+    ref = oc.rectify_f32c1(ch, 1.0 / ratio, axs, frames, fill=-3.0)
+    for gather in ("auto", "direct"):
+        got = cc.warp(c, 0, _dev(frames), ratio, axs, fill=-3.0, gather=gather).cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.array_equal(got[ok].view(np.uint32), ref[ok].view(np.uint32)), (kind, gather)   # bits: -0 vs +0 too
+
+
 @pytest.mark.parametrize("sz", [(2160, 3840), (1080, 1920), (360, 640), (131, 77), (16, 5)])
 def test_rectify_u8c3_bit_exact(cc, sz):
     intr = camera_for(sz)
