@@ -179,20 +179,25 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     int s = 0;
     uint32_t phase = 0;
     int4 pos = make_int4(0, 0, 0, 0);
-    int frames_left = 0;
+    int frames_left = 0, frame_z = 0;
+    float* o_cur = dst;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
-        // the slot is read on a unit's first frame only; the frames of the unit are counted down in
-        // (warp-uniform) registers -- no LDS + two dependent branches in front of every frame
-        if (kPosTrack ? frames_left == 0 : true) {
+        // CAMCAL_POS_TRACK: the slot is read on a unit's first frame only; frame index and frames left
+        // are carried in warp-uniform registers (declared uniform through a shuffle) -- no LDS + two
+        // dependent branches in front of every frame
+        if (!kPosTrack || frames_left == 0) {
             pos = ring.pos[s];
             if (pos.z < 0) break;
-            frames_left = kPosTrack ? pos.w : 0;
+            if (kPosTrack) {
+                frame_z = __shfl_sync(0xffffffffu, pos.z, 0);
+                frames_left = __shfl_sync(0xffffffffu, pos.w, 0);
+            } else {
+                frame_z = pos.z;
+            }
         } else {
-            pos.z += 1;
             pos.w = 0;
         }
-        if (kPosTrack) --frames_left;
         if (pos.w) {                                   // ---- first frame of a unit: build the map
             const TileHdr* h = &ring.hdr[s];
             const int a_w = pos.x * kT;
@@ -261,8 +266,10 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         }
 
         // ---- every frame of the unit: gather, blend, store
-        const float* sframe = src + (long long)pos.z * g.frame_stride;
-        float* o = dst + (long long)pos.z * g.frame_stride + off0;
+        const float* sframe = src + (long long)frame_z * g.frame_stride;
+        // kPosTrack: a running output pointer (set on the unit's first frame, one 64-bit add per frame)
+        if (!kPosTrack || pos.w) o_cur = dst + (long long)frame_z * g.frame_stride + off0;
+        float* o = o_cur;
         const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
         const uint32_t sbase1 = sbase + box_pitch_b;    // one uniform base per source line: LDS [R + UR + imm], no per-pixel add
         auto border = [&](float* o) {
@@ -393,6 +400,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         }
         __syncwarp();
         if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
+        if (kPosTrack) { --frames_left; ++frame_z; o_cur += g.frame_stride; }
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }

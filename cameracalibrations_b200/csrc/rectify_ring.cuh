@@ -42,7 +42,7 @@ __device__ __forceinline__ void producer_wait(uint64_t* bar, uint32_t parity) {
 // in a 96-register kernel; kept as a knob); CAMCAL_ELECT: the arriving lane chosen with ELECT
 // instead of a lane-id compare (no S2R per frame; neutral)
 #ifndef CAMCAL_POS_TRACK
-#define CAMCAL_POS_TRACK 0
+#define CAMCAL_POS_TRACK 1
 #endif
 #ifndef CAMCAL_ELECT
 #define CAMCAL_ELECT 1
@@ -50,7 +50,7 @@ __device__ __forceinline__ void producer_wait(uint64_t* bar, uint32_t parity) {
 constexpr bool kPosTrack = CAMCAL_POS_TRACK != 0, kElectArrive = CAMCAL_ELECT != 0;
 // L2 eviction hint of the staged boxes (tma.cuh): 0 none, 1 evict_last, 2 evict_first, 3 evict_normal
 #ifndef CAMCAL_TMA_L2
-#define CAMCAL_TMA_L2 0
+#define CAMCAL_TMA_L2 1
 #endif
 __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
     uint32_t u = 0;

@@ -242,6 +242,10 @@ rectify_u8c3_direct_kernel(const __grid_constant__ RectExact pe, const __grid_co
 #ifndef CAMCAL_U8_DEBUG
 #define CAMCAL_U8_DEBUG 0
 #endif
+#ifndef CAMCAL_U8_BORDER
+#define CAMCAL_U8_BORDER 1
+#endif
+constexpr bool kBorderUnrolledU8 = CAMCAL_U8_BORDER != 0;
 constexpr int kU8Load = CAMCAL_U8_LOAD;
 constexpr bool kU8Bytes = CAMCAL_U8_LOAD == 1;      // rel[] is a byte address (no word alignment / selector)
 constexpr bool kU8Mixed = CAMCAL_U8_LOAD >= 3;   // words for line i2, bytes for (part of) line i2+1
@@ -410,20 +414,24 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     int s = 0;
     uint32_t phase = 0;
     int4 pos = make_int4(0, 0, 0, 0);
-    int frames_left = 0;
+    int frames_left = 0, frame_z = 0;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
-        // the slot is read on a unit's first frame only; the frames of the unit are counted down in
-        // (warp-uniform) registers -- no LDS + two dependent branches in front of every frame
-        if (kPosTrack ? frames_left == 0 : true) {
+        // CAMCAL_POS_TRACK: the slot is read on a unit's first frame only; frame index and frames left
+        // are carried in warp-uniform registers (declared uniform through a shuffle) -- no LDS + two
+        // dependent branches in front of every frame
+        if (!kPosTrack || frames_left == 0) {
             pos = ring.pos[s];
             if (pos.z < 0) break;
-            frames_left = kPosTrack ? pos.w : 0;
+            if (kPosTrack) {
+                frame_z = __shfl_sync(0xffffffffu, pos.z, 0);
+                frames_left = __shfl_sync(0xffffffffu, pos.w, 0);
+            } else {
+                frame_z = pos.z;
+            }
         } else {
-            pos.z += 1;
             pos.w = 0;
         }
-        if (kPosTrack) --frames_left;
         if (pos.w) {                                   // ---- first frame of a unit: build the map
             const TileHdr* h = &ring.hdr[s];
             const int a_w = pos.x * kT;
@@ -503,8 +511,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
 
         // ---- every frame of the unit: gather, blend, store
-        const uint8_t* sframe = src + (long long)pos.z * g.frame_stride * 3;
-        uint8_t* oline = dst + (long long)pos.z * g.frame_stride * 3 + off0;
+        const uint8_t* sframe = src + (long long)frame_z * g.frame_stride * 3;
+        uint8_t* oline = dst + (long long)frame_z * g.frame_stride * 3 + off0;
         const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
         const uint32_t sbase1 = sbase + box_pitch_b;
         if (all_staged) {
@@ -559,6 +567,43 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     }
                 }
             }
+        } else if (kBorderUnrolledU8) {
+            // border tiles: staged and fill pixels unrolled over the map (static indices), byte stores;
+            // then one rolled pass for the generic remainder (it needs no map entry).  The rolled
+            // compare-chain loop below cost ~100 instructions per pixel.
+            uint8_t* o = oline + lane_id * 3;
+#pragma unroll
+            for (int e = 0; e < LPW; ++e, o += pitch3) {
+                const uint32_t bit = 1u << e;
+                if (m_skip & bit) continue;
+                if (m_staged & bit) {
+                    const uint32_t sel = kU8Bytes ? 0u : selv[e];
+                    const TapF t = load_taps(sbase + rel[e], sbase1 + rel[e], sel, kU8Mixed ? sbase1 + relb[e] : 0u);
+                    const float f00 = (e & 1) ? w00[e / 2].y : w00[e / 2].x, f10 = (e & 1) ? w10[e / 2].y : w10[e / 2].x;
+                    const float f01 = (e & 1) ? w01[e / 2].y : w01[e / 2].x, f11 = (e & 1) ? w11[e / 2].y : w11[e / 2].x;
+                    uint32_t v, vq;
+                    float2 dm1;
+                    blend_px2<EXACT>(t, t, bc2(f00), bc2(f10), bc2(f01), bc2(f11), v, vq, dm1);
+                    if (EXACT && dm1.x > kCertThr) {
+                        const uint32_t bo = rel[e] + (kU8Bytes ? 0u : (sel & 3u));
+                        v = reblend_exact_u8(&pe, &g, a, b0 + e, sbase + bo, sbase1 + bo);
+                    }
+                    store_rgb(o, v);
+                } else if (m_fill & bit) {
+                    store_rgb(o, fill);
+                }
+            }
+            const uint32_t m_gen = ~(m_staged | m_fill | m_skip) & ((1u << LPW) - 1u);
+            if (m_gen) {
+                RowTermD rtd;
+                RowTermF rtf;
+                if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+                uint8_t* og = oline + lane_id * 3;
+#pragma unroll 1
+                for (int e = 0; e < LPW; ++e, og += pitch3)
+                    if ((m_gen >> e) & 1u)
+                        store_rgb(og, sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b0 + e, fill));
+            }
         } else {
             // border tiles: per-pixel class, byte stores
             uint8_t* o = oline + lane_id * 3;
@@ -598,6 +643,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
         __syncwarp();
         if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
+        if (kPosTrack) { --frames_left; ++frame_z; }
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }
