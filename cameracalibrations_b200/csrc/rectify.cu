@@ -50,7 +50,7 @@ constexpr int kTLmax = 32;             // most lines of a tile (sizes the per-st
 #define CAMCAL_FG_U8_EXACT 16
 #endif
 #ifndef CAMCAL_FG_U8_FAST
-#define CAMCAL_FG_U8_FAST 12
+#define CAMCAL_FG_U8_FAST 16
 #endif
 constexpr int kFGf32Exact = CAMCAL_FG_F32_EXACT, kFGf32Fast = CAMCAL_FG_F32_FAST, kFGu8Exact = CAMCAL_FG_U8_EXACT, kFGu8Fast = CAMCAL_FG_U8_FAST;
 #ifndef CAMCAL_TL_U8

@@ -403,8 +403,16 @@ __device__ __noinline__ uint32_t reblend_exact_u8(const RectExact* pe, const Rec
     return out;
 }
 
+// CAMCAL_U8_MAXNREG_FAST > 0: cap the FP32-coordinate variant with __maxnreg__ instead of a min-blocks bound
+#ifndef CAMCAL_U8_MAXNREG_FAST
+#define CAMCAL_U8_MAXNREG_FAST 0
+#endif
 template <bool EXACT>
+#if CAMCAL_U8_MAXNREG_FAST > 0
+__global__ void __launch_bounds__(kConsumerThreads + 32) __maxnreg__(EXACT ? 65536 / ((kConsumerThreads + 32) * kMinBlocksU8Exact) / 8 * 8 : CAMCAL_U8_MAXNREG_FAST)
+#else
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksU8Exact : kMinBlocksU8)
+#endif
 rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
                     const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
                     const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
@@ -556,6 +564,8 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 
         // ---- every frame of the unit: gather, blend, store
         const uint8_t* sframe = src + (long long)frame_z * g.frame_stride * 3;
+        // (a running output pointer, as in the f32c1 kernel, costs this one registers: ptxas goes from
+        // 96 to 104 and the fast variant from 4 to 3 CTAs per SM -- measured 0.204 vs 0.194 ms on c3)
         uint8_t* oline = dst + (long long)frame_z * g.frame_stride * 3 + off0;
         const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
         const uint32_t sbase1 = sbase + box_pitch_b;
