@@ -47,6 +47,21 @@ __device__ __forceinline__ float sample_direct_f32(const RectExact& pe, const Re
     }
 }
 
+// output store flavour (tuning knob): 0 st.global.cs, 1 .wt, 2 .cg, 3 default (.wb), 4 .cs + L2 evict_first hint
+#ifndef CAMCAL_F32_STORE
+#define CAMCAL_F32_STORE 0
+#endif
+__device__ __forceinline__ void st_out(float* p, float v) {
+    if (CAMCAL_F32_STORE == 1) __stwt(p, v);
+    else if (CAMCAL_F32_STORE == 2) __stcg(p, v);
+    else if (CAMCAL_F32_STORE == 3) *p = v;
+    else if (CAMCAL_F32_STORE == 4) {
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
+    } else __stcs(p, v);
+}
+
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -140,8 +155,17 @@ __device__ __forceinline__ double bilerp_scaled(double a00, double a10, double a
     return fma(d1, hi, e1 * lo);
 }
 
+// CAMCAL_F32_MAXNREG_FAST > 0: cap the FP32-coordinate variant with __maxnreg__ (5 CTAs of 5 warps put 7
+// warps on one scheduler: 7 * 32 * 72 registers is what its 16 K registers hold, 80 is not)
+#ifndef CAMCAL_F32_MAXNREG_FAST
+#define CAMCAL_F32_MAXNREG_FAST 0
+#endif
 template <bool EXACT>
+#if CAMCAL_F32_MAXNREG_FAST > 0
+__global__ void __launch_bounds__(kConsumerThreads + 32) __maxnreg__(EXACT ? 65536 / ((kConsumerThreads + 32) * kMinBlocksExact) / 8 * 8 : CAMCAL_F32_MAXNREG_FAST)
+#else
 __global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
+#endif
 rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
                      const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
                      const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
@@ -379,7 +403,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                         __stcs(o, (float)bilerp_e((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
                                                   wd1[e], we1[e], wd2[e], we2[e]));
                     } else {
-                        __stcs(o, (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
+                        st_out(o, (float)bilerp((double)a00[e], (double)a10[e], (double)a01[e], (double)a11[e],
                                                 wd1[e], wd2[e]));
                     }
                     o += pitch;
@@ -391,7 +415,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                                                   make_float2(a10[2 * hh], a10[2 * hh + 1]),
                                                   make_float2(a01[2 * hh], a01[2 * hh + 1]),
                                                   make_float2(a11[2 * hh], a11[2 * hh + 1]), wf1[hh], wf2[hh]);
-                    __stcs(o, v.x); __stcs(o + pitch, v.y);
+                    st_out(o, v.x); st_out(o + pitch, v.y);
                     o += 2 * pitch;
                 }
             }
