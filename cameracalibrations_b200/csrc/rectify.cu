@@ -654,7 +654,8 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     if (tma) {
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
         cfg.widen_mul = 0x20000000u;
-        const size_t smem = (size_t)cfg.stages * cfg.box_bytes;
+        cfg.stages = std::max(2, cfg.stages / kF32FramesPerStage);       // a stage holds kF32FramesPerStage boxes
+        const size_t smem = (size_t)cfg.stages * kF32FramesPerStage * cfg.box_bytes;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, 0, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)
                         : persistent_grid(ctx, 1, rectify_f32c1_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;

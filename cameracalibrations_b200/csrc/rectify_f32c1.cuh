@@ -74,6 +74,15 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
     return v;
 }
 
+// CAMCAL_F32_PAIR 1: two frames per ring stage.  The consumers pay the hand-over (barrier wait, stage
+// addresses, arrive) once per PAIR of frames, and the exact blend computes 1 - d1, 1 - d2 once for both
+// (7 instead of 8 FP64 instructions per pixel and frame).
+#ifndef CAMCAL_F32_PAIR
+#define CAMCAL_F32_PAIR 1
+#endif
+constexpr int kF32FramesPerStage = CAMCAL_F32_PAIR != 0 ? 2 : 1;
+static_assert(kF32FramesPerStage == 1 || kPosTrack, "pairs of frames need the frame counters (CAMCAL_POS_TRACK)");
+
 #ifndef CAMCAL_F32_BORDER
 #define CAMCAL_F32_BORDER 1
 #endif
@@ -173,6 +182,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                      const float* __restrict__ src, float* __restrict__ dst, float fill) {
     constexpr int TL = kTLf;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
+    constexpr int NF = kF32FramesPerStage;        // frames per ring stage
     static_assert(LPW % 2 == 0 && LPW <= 16, "pairs of lines; masks are 16 bits");
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemRing ring;
@@ -181,7 +191,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        producer_loop<EXACT, TL, 1>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
+        producer_loop<EXACT, TL, 1, kF32FramesPerStage>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 
@@ -291,11 +301,13 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
         // ---- every frame of the unit: gather, blend, store
         const float* sframe = src + (long long)frame_z * g.frame_stride;
+        // NF == 2: this stage holds frames frame_z and frame_z + 1 (the same frame twice at the odd end of a unit)
+        const long long pair_off = (NF == 2 && frames_left > 1) ? g.frame_stride : 0;
         // kPosTrack: a running output pointer (set on the unit's first frame, one 64-bit add per frame)
         if (!kPosTrack || pos.w) o_cur = dst + (long long)frame_z * g.frame_stride + off0;
         float* o = o_cur;
-        const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
-        const uint32_t sbase1 = sbase + box_pitch_b;    // one uniform base per source line: LDS [R + UR + imm], no per-pixel add
+        uint32_t sbase = stage0 + (uint32_t)(s * NF) * (uint32_t)cfg.box_bytes;
+        uint32_t sbase1 = sbase + box_pitch_b;    // one uniform base per source line: LDS [R + UR + imm], no per-pixel add
         auto border = [&](float* o) {
             // border tiles (and frames whose taps the integer widening cannot take): per-pixel class.
             // CAMCAL_F32_BORDER 1: staged and fill pixels unrolled (static indices into the map), then
@@ -365,7 +377,45 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             }
             }
         };
-        if (all_staged) {
+        if (all_staged && NF == 2 && !(EXACT && (kWiden || kKeepE))) {
+            // two frames with one map: taps of frame A at sbase, of frame B one box further
+            const uint32_t tbase = sbase + (uint32_t)cfg.box_bytes, tbase1 = sbase1 + (uint32_t)cfg.box_bytes;
+            float* oA = o;
+            float* oB = o + pair_off;
+            if (EXACT) {
+#pragma unroll
+                for (int e = 0; e < LPW; ++e) {
+                    const uint32_t r = rel[e];
+#ifdef CAMCAL_CHECK_BOUNDS
+                    if (r + box_pitch_b + 8u > (uint32_t)cfg.box_bytes || (r & 3u)) __trap();
+#endif
+                    const float a00 = lds_f32(sbase + r), a10 = lds_f32_off<4>(sbase + r);
+                    const float a01 = lds_f32(sbase1 + r), a11 = lds_f32_off<4>(sbase1 + r);
+                    const float c00 = lds_f32(tbase + r), c10 = lds_f32_off<4>(tbase + r);
+                    const float c01 = lds_f32(tbase1 + r), c11 = lds_f32_off<4>(tbase1 + r);
+                    const double d1 = wd1[e], d2 = wd2[e], e1 = 1.0 - d1, e2 = 1.0 - d2;
+                    st_out(oA, (float)bilerp_e((double)a00, (double)a10, (double)a01, (double)a11, d1, e1, d2, e2));
+                    st_out(oB, (float)bilerp_e((double)c00, (double)c10, (double)c01, (double)c11, d1, e1, d2, e2));
+                    oA += pitch; oB += pitch;
+                }
+            } else {
+#pragma unroll
+                for (int hh = 0; hh < LPW / 2; ++hh) {
+                    const uint32_t r0 = rel[2 * hh], r1 = rel[2 * hh + 1];
+                    const float2 vA = bilerp_fast2(make_float2(lds_f32(sbase + r0), lds_f32(sbase + r1)),
+                                                   make_float2(lds_f32_off<4>(sbase + r0), lds_f32_off<4>(sbase + r1)),
+                                                   make_float2(lds_f32(sbase1 + r0), lds_f32(sbase1 + r1)),
+                                                   make_float2(lds_f32_off<4>(sbase1 + r0), lds_f32_off<4>(sbase1 + r1)), wf1[hh], wf2[hh]);
+                    const float2 vB = bilerp_fast2(make_float2(lds_f32(tbase + r0), lds_f32(tbase + r1)),
+                                                   make_float2(lds_f32_off<4>(tbase + r0), lds_f32_off<4>(tbase + r1)),
+                                                   make_float2(lds_f32(tbase1 + r0), lds_f32(tbase1 + r1)),
+                                                   make_float2(lds_f32_off<4>(tbase1 + r0), lds_f32_off<4>(tbase1 + r1)), wf1[hh], wf2[hh]);
+                    st_out(oA, vA.x); st_out(oA + pitch, vA.y);
+                    st_out(oB, vB.x); st_out(oB + pitch, vB.y);
+                    oA += 2 * pitch; oB += 2 * pitch;
+                }
+            }
+        } else if (all_staged) {
             float a00[LPW], a10[LPW], a01[LPW], a11[LPW];
 #pragma unroll
             for (int e = 0; e < LPW; ++e) {
@@ -422,9 +472,15 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         } else {
             border(o);
         }
+        if (NF == 2 && pair_off != 0 && !(all_staged && !(EXACT && (kWiden || kKeepE)))) {
+            // second frame of the stage through the per-frame paths (border tiles; the knob variants)
+            sbase += (uint32_t)cfg.box_bytes; sbase1 += (uint32_t)cfg.box_bytes;
+            sframe += g.frame_stride;
+            border(o_cur + pair_off);
+        }
         __syncwarp();
         if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
-        if (kPosTrack) { --frames_left; ++frame_z; o_cur += g.frame_stride; }
+        if (kPosTrack) { frames_left = max(frames_left - NF, 0); frame_z += NF; o_cur += NF * g.frame_stride; }
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }
