@@ -705,7 +705,8 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
     if (tma) {
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLu, exact ? kFGu8Exact : kFGu8Fast))) return rc;
         // + 16: the word-granular gather may read the aligned words that hold the last tap bytes
-        const size_t smem = (size_t)cfg.stages * cfg.box_bytes + 16;
+        cfg.stages = std::max(2, cfg.stages / kU8FramesPerStage);        // a stage holds kU8FramesPerStage boxes
+        const size_t smem = (size_t)cfg.stages * kU8FramesPerStage * cfg.box_bytes + 16;
         uint32_t gsz = 0;
         if ((rc = exact ? persistent_grid(ctx, 2, rectify_u8c3_kernel<true>, smem, cfg, plan, true, &gsz)
                         : persistent_grid(ctx, 3, rectify_u8c3_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;

@@ -242,6 +242,14 @@ rectify_u8c3_direct_kernel(const __grid_constant__ RectExact pe, const __grid_co
 #ifndef CAMCAL_U8_DEBUG
 #define CAMCAL_U8_DEBUG 0
 #endif
+// CAMCAL_U8_PAIR 1: two frames per ring stage (one hand-over per pair of frames, as in rectify_f32c1.cuh).
+// Measured SLOWER here (c3 fast 0.199 vs 0.195 ms, exact 0.354 vs 0.304): the loop over the stage's
+// frames costs registers (fast 96 -> 128, exact spills or 136 = two CTAs per SM); kept as a knob.
+#ifndef CAMCAL_U8_PAIR
+#define CAMCAL_U8_PAIR 0
+#endif
+constexpr int kU8FramesPerStage = CAMCAL_U8_PAIR != 0 ? 2 : 1;
+static_assert(kU8FramesPerStage == 1 || kPosTrack, "pairs of frames need the frame counters (CAMCAL_POS_TRACK)");
 #ifndef CAMCAL_U8_BORDER
 #define CAMCAL_U8_BORDER 1
 #endif
@@ -422,6 +430,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     constexpr int TL = kTLu;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
     constexpr int NP = LPW / 2;                   // pairs of lines
+    constexpr int NF = kU8FramesPerStage;         // frames per ring stage
     constexpr bool IDP = !EXACT && kU8FastIdp && !kU8Bytes;   // fast variant: integer blend on vertical byte pairs
     static_assert(LPW % 2 == 0 && LPW <= 16, "pairs of lines; masks are 16 bits");
     extern __shared__ __align__(128) uint8_t stage_mem[];
@@ -431,7 +440,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        producer_loop<EXACT, TL, 1>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
+        producer_loop<EXACT, TL, 1, kU8FramesPerStage>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 
@@ -563,11 +572,16 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         }
 
         // ---- every frame of the unit: gather, blend, store
-        const uint8_t* sframe = src + (long long)frame_z * g.frame_stride * 3;
+        // NF == 2: the stage holds frames frame_z and frame_z + 1 (only one at the odd end of a unit); the
+        // frames of a stage go through the same code one after the other (rolled: the hot block is long)
+        const int nf_here = (NF == 2 && frames_left > 1) ? 2 : 1;
+#pragma unroll 1
+        for (int hf = 0; hf < nf_here; ++hf) {
+        const uint8_t* sframe = src + (long long)(frame_z + hf) * g.frame_stride * 3;
         // (a running output pointer, as in the f32c1 kernel, costs this one registers: ptxas goes from
         // 96 to 104 and the fast variant from 4 to 3 CTAs per SM -- measured 0.204 vs 0.194 ms on c3)
-        uint8_t* oline = dst + (long long)frame_z * g.frame_stride * 3 + off0;
-        const uint32_t sbase = stage0 + (uint32_t)s * (uint32_t)cfg.box_bytes;
+        uint8_t* oline = dst + (long long)(frame_z + hf) * g.frame_stride * 3 + off0;
+        const uint32_t sbase = stage0 + (uint32_t)(s * NF + hf) * (uint32_t)cfg.box_bytes;
         const uint32_t sbase1 = sbase + box_pitch_b;
         if (all_staged) {
             uint32_t* ow = reinterpret_cast<uint32_t*>(oline) + widx;
@@ -713,9 +727,10 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 store_rgb(o, v);
             }
         }
+        }   // frames of the stage
         __syncwarp();
         if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
-        if (kPosTrack) { --frames_left; ++frame_z; }
+        if (kPosTrack) { frames_left = max(frames_left - NF, 0); frame_z += NF; }
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
 }
