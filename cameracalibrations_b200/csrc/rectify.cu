@@ -540,7 +540,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
 // raises it (a smaller plan must not lower the limit under a cached larger one, whichever context
 // of the process made either call).
 static std::mutex g_smem_mu;
-static size_t g_smem_attr[64][4];
+static size_t g_smem_attr[64][8];
 template <typename K>
 static int set_smem(cc_ctx* ctx, int kslot, K kernel, size_t bytes) {
     if (bytes <= 32 * 1024) return CC_OK;     // static smem (barriers + headers) counts against the 48 KB default too
@@ -654,17 +654,26 @@ int launch_rectify_f32c1(cc_ctx* ctx, const ChainD& chd, double ratio, const int
     if (tma) {
         if ((rc = unit_cfg(ctx, &cfg, sz1, sz2, nframes, kT, kTLf, exact ? kFGf32Exact : kFGf32Fast))) return rc;
         cfg.widen_mul = 0x20000000u;
-        cfg.stages = std::max(2, cfg.stages / kF32FramesPerStage);       // a stage holds kF32FramesPerStage boxes
-        const size_t smem = (size_t)cfg.stages * kF32FramesPerStage * cfg.box_bytes;
+        // two frames per ring stage when the ring holds at least four boxes (large boxes keep one) and the
+        // units have at least two frames (single frames, e.g. the per-view launches of cc_rectify_*_views, keep one)
+        const int nf = (kF32FramesPerStage == 2 && cfg.stages >= 4 && cfg.fg >= 2) ? 2 : 1;
+        cfg.stages /= nf;
+        const size_t smem = (size_t)cfg.stages * nf * cfg.box_bytes;
         uint32_t gsz = 0;
-        if ((rc = exact ? persistent_grid(ctx, 0, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)
-                        : persistent_grid(ctx, 1, rectify_f32c1_kernel<false>, smem, cfg, plan, false, &gsz))) return rc;
+        if (nf == 2) rc = exact ? persistent_grid(ctx, 0, rectify_f32c1_kernel<true>, smem, cfg, plan, true, &gsz)
+                                : persistent_grid(ctx, 1, rectify_f32c1_kernel<false>, smem, cfg, plan, false, &gsz);
+        else         rc = exact ? persistent_grid(ctx, 4, rectify_f32c1_single_kernel<true>, smem, cfg, plan, true, &gsz)
+                                : persistent_grid(ctx, 5, rectify_f32c1_single_kernel<false>, smem, cfg, plan, false, &gsz);
+        if (rc) return rc;
         RectSched* sched = nullptr;
         if ((rc = sched_acquire(ctx, st, &sched))) return rc;
-        if (exact)
-            rectify_f32c1_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
-        else
-            rectify_f32c1_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+        if (nf == 2) {
+            if (exact) rectify_f32c1_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+            else       rectify_f32c1_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+        } else {
+            if (exact) rectify_f32c1_single_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+            else       rectify_f32c1_single_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(tmap, pe, pf, g, cfg, plan->d_hdr, plan->d_q2, sched, src, dst, fill);
+        }
         sched_release(ctx, st);
     } else {
         int lines = 0;

@@ -169,20 +169,14 @@ __device__ __forceinline__ double bilerp_scaled(double a00, double a10, double a
 #ifndef CAMCAL_F32_MAXNREG_FAST
 #define CAMCAL_F32_MAXNREG_FAST 0
 #endif
-template <bool EXACT>
-#if CAMCAL_F32_MAXNREG_FAST > 0
-__global__ void __launch_bounds__(kConsumerThreads + 32) __maxnreg__(EXACT ? 65536 / ((kConsumerThreads + 32) * kMinBlocksExact) / 8 * 8 : CAMCAL_F32_MAXNREG_FAST)
-#else
-__global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
-#endif
-rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
-                     const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
-                     const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
-                     const double* __restrict__ q2tab, RectSched* __restrict__ sched,
-                     const float* __restrict__ src, float* __restrict__ dst, float fill) {
+// the kernel body; NF = frames per ring stage (the two __global__ wrappers are below)
+template <bool EXACT, int NF>
+__device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, const RectExact& pe, const RectFast& pf,
+                                                   const RectGeom& g, const TileCfg& cfg, const TileHdr* __restrict__ plan,
+                                                   const double* __restrict__ q2tab, RectSched* __restrict__ sched,
+                                                   const float* __restrict__ src, float* __restrict__ dst, float fill) {
     constexpr int TL = kTLf;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
-    constexpr int NF = kF32FramesPerStage;        // frames per ring stage
     static_assert(LPW % 2 == 0 && LPW <= 16, "pairs of lines; masks are 16 bits");
     extern __shared__ __align__(128) uint8_t stage_mem[];
     __shared__ SmemRing ring;
@@ -191,7 +185,7 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        producer_loop<EXACT, TL, 1, kF32FramesPerStage>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
+        producer_loop<EXACT, TL, 1, NF>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 
@@ -301,8 +295,9 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
 
         // ---- every frame of the unit: gather, blend, store
         const float* sframe = src + (long long)frame_z * g.frame_stride;
-        // NF == 2: this stage holds frames frame_z and frame_z + 1 (the same frame twice at the odd end of a unit)
-        const long long pair_off = (NF == 2 && frames_left > 1) ? g.frame_stride : 0;
+        // NF == 2: this stage holds frames frame_z and frame_z + 1 (only frame_z at the odd end of a unit)
+        const bool two = NF == 2 && frames_left > 1;
+        constexpr bool kPairBlock = NF == 2 && !(EXACT && (kWiden || kKeepE));   // the two-frame hot block exists
         // kPosTrack: a running output pointer (set on the unit's first frame, one 64-bit add per frame)
         if (!kPosTrack || pos.w) o_cur = dst + (long long)frame_z * g.frame_stride + off0;
         float* o = o_cur;
@@ -377,11 +372,11 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             }
             }
         };
-        if (all_staged && NF == 2 && !(EXACT && (kWiden || kKeepE))) {
+        if (kPairBlock && all_staged && two) {
             // two frames with one map: taps of frame A at sbase, of frame B one box further
             const uint32_t tbase = sbase + (uint32_t)cfg.box_bytes, tbase1 = sbase1 + (uint32_t)cfg.box_bytes;
             float* oA = o;
-            float* oB = o + pair_off;
+            float* oB = o + g.frame_stride;
             if (EXACT) {
 #pragma unroll
                 for (int e = 0; e < LPW; ++e) {
@@ -472,17 +467,43 @@ rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         } else {
             border(o);
         }
-        if (NF == 2 && pair_off != 0 && !(all_staged && !(EXACT && (kWiden || kKeepE)))) {
-            // second frame of the stage through the per-frame paths (border tiles; the knob variants)
+        if (two && !(kPairBlock && all_staged)) {
+            // second frame of the stage through the per-frame path (border tiles; the knob variants)
             sbase += (uint32_t)cfg.box_bytes; sbase1 += (uint32_t)cfg.box_bytes;
             sframe += g.frame_stride;
-            border(o_cur + pair_off);
+            border(o_cur + g.frame_stride);
         }
         __syncwarp();
         if (kElectArrive ? elect_one() : lane_id == 0) mbar_arrive(&ring.empty[s]);
         if (kPosTrack) { frames_left = max(frames_left - NF, 0); frame_z += NF; o_cur += NF * g.frame_stride; }
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
+}
+
+#if CAMCAL_F32_MAXNREG_FAST > 0
+#define CAMCAL_F32_KERNEL_ATTR(EXACT) __launch_bounds__(kConsumerThreads + 32) __maxnreg__(EXACT ? 65536 / ((kConsumerThreads + 32) * kMinBlocksExact) / 8 * 8 : CAMCAL_F32_MAXNREG_FAST)
+#else
+#define CAMCAL_F32_KERNEL_ATTR(EXACT) __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksExact : kMinBlocks)
+#endif
+// two frames per ring stage (the default: rings of at least four boxes)
+template <bool EXACT>
+__global__ void CAMCAL_F32_KERNEL_ATTR(EXACT)
+rectify_f32c1_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
+                     const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
+                     const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
+                     const double* __restrict__ q2tab, RectSched* __restrict__ sched,
+                     const float* __restrict__ src, float* __restrict__ dst, float fill) {
+    rectify_f32c1_body<EXACT, kF32FramesPerStage>(tmap, pe, pf, g, cfg, plan, q2tab, sched, src, dst, fill);
+}
+// one frame per stage: large boxes (strongly tilted or magnifying views), whose ring holds two or three
+template <bool EXACT>
+__global__ void CAMCAL_F32_KERNEL_ATTR(EXACT)
+rectify_f32c1_single_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
+                            const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
+                            const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
+                            const double* __restrict__ q2tab, RectSched* __restrict__ sched,
+                            const float* __restrict__ src, float* __restrict__ dst, float fill) {
+    rectify_f32c1_body<EXACT, 1>(tmap, pe, pf, g, cfg, plan, q2tab, sched, src, dst, fill);
 }
 
 }  // namespace cc

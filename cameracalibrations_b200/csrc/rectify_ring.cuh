@@ -62,8 +62,8 @@ __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
 // A unit is (strip x, tile y, frame group): the producer publishes one slot per FRAME of the
 // group -- pos = (x, y, frame, number of frames of the unit on its first frame, else 0) -- the
 // consumers read the slot on a unit's first frame only (CAMCAL_POS_TRACK) and count the frames down.
-// NF: frames per ring stage (2: a stage holds the boxes of two consecutive frames of the unit -- the
-// last one twice when the unit has an odd number of frames -- so the consumers pay one hand-over per pair)
+// NF: frames per ring stage (2: a stage holds the boxes of two consecutive frames of the unit -- one at
+// the odd end of a unit -- so the consumers pay one hand-over per pair)
 template <bool EXACT, int TL, int PXB, int NF = 1>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const RectGeom& g, const TileCfg& cfg,
                                               const TileHdr* __restrict__ plan,
@@ -106,13 +106,14 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const Rec
             if (lane_id == 12) ring->pos[s] = make_int4(x, y, f, f == f0 ? f1 - f0 : 0);   // .w: frames of the unit, on its first frame
             __syncwarp();
             if (lane_id == 0) {
-                mbar_arrive_expect_tx(&ring->full[s], (uint32_t)cfg.box_bytes * NF);
+                const int nload = min(NF, f1 - f);             // the odd end of a unit: one box
+                mbar_arrive_expect_tx(&ring->full[s], (uint32_t)cfg.box_bytes * nload);
 #pragma unroll
                 for (int j = 0; j < NF; ++j) {
+                    if (j >= nload) break;
                     uint8_t* box = stage_mem + ((size_t)s * NF + j) * cfg.box_bytes;
-                    const int fj = min(f + j, f1 - 1);
-                    if (CAMCAL_TMA_L2 != 0) tma_load_3d_hint(box, tmap, &ring->full[s], x0 * PXB, y0, fj, policy);
-                    else tma_load_3d(box, tmap, &ring->full[s], x0 * PXB, y0, fj);
+                    if (CAMCAL_TMA_L2 != 0) tma_load_3d_hint(box, tmap, &ring->full[s], x0 * PXB, y0, f + j, policy);
+                    else tma_load_3d(box, tmap, &ring->full[s], x0 * PXB, y0, f + j);
                 }
             }
             if (++s == cfg.stages) { s = 0; phase ^= 1; }
