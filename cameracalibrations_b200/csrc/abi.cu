@@ -197,9 +197,20 @@ static int rectify_host(cc_ctx* ctx, const PX* src, PX* dst, int sz1, int sz2, s
     if (per < 1) per = 1;
     if (per > nframes) per = nframes;
     const bool dense = frame_stride == frame_elems && pitch == (size_t)sz1;
-    for (int f0 = 0, it = 0; f0 < nframes; f0 += per, ++it) {
+    // The first chunk's upload and the last chunk's download overlap with nothing: the batch starts with
+    // chunks of 1, 2, 4 ... frames and ends with ... 4, 2, 1 (CAMCAL_CHUNK_RAMP=0: uniform chunks), so the
+    // exposed head and tail are one frame each instead of one 32 MB chunk each.
+    bool ramp = true;
+    if (const char* e = getenv("CAMCAL_CHUNK_RAMP")) ramp = atoi(e) != 0;   // tuning knob
+    int ramp_frames = 0, ramp_steps = 0;                     // frames / chunks of one ramp: 1 + 2 + ... (< per)
+    for (int c = 1; ramp && c < per; c *= 2) { ramp_frames += c; ++ramp_steps; }
+    if (2 * ramp_frames + per > nframes) ramp_frames = ramp_steps = 0;
+    for (int f0 = 0, it = 0, m = 0; f0 < nframes; f0 += m, ++it) {
         const int k = it % cc_ctx::NSLOT;
-        const int m = (nframes - f0) < per ? (nframes - f0) : per;
+        const int left = nframes - f0;
+        if (it < ramp_steps) m = 1 << it;                                    // head: 1, 2, 4 ...
+        else if (left > ramp_frames) m = std::min(per, left - ramp_frames);  // body
+        else { m = 1; while (2 * m - 1 < left) m *= 2; }                     // tail: left = 2m - 1 -> m, ... 2, 1
         // +64 bytes: vector gathers may touch the aligned word holding the last texel
         if ((rc = ensure_slot(ctx, k, per * frame_bytes + 64, per * frame_bytes + 64))) return rc;
         cudaStream_t st = ctx->pipe_stream[k];
