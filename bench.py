@@ -478,7 +478,7 @@ def extras(cc, torch, dev, c2cal, args):
         ex[f"rectify_views_64x1080p_{coord}"] = {
             "mpix_per_s": npx / (ms * 1e-3) / 1e6, "ms": ms, "hbm_frac": 8 * npx / (ms * 1e-3) / 1e9 / peak,
             "first_call_ms": first_ms,
-            "note": "64 frames, 64 different views, one call (64 launches, tile plans cached after the first call); "
+            "note": "64 frames, 64 different views, one call = ONE launch (rectify_f32c1_views_kernel; tile plans cached after the first call); "
                     "first_call_ms includes building and uploading the 64 tile plans on the host"}
     del src, dst
     # ingest: compressed JPEG bytes -> device frames -> the views call, nothing returns to

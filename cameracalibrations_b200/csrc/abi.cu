@@ -2,6 +2,7 @@
 // argument checking, per-device context, and the chunked host pipeline behind the
 // *_host entry points.  No compute lives here and nothing here can fall back to the CPU.
 #include <algorithm>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -39,6 +40,11 @@ int launch_rectify_f32c1(cc_ctx*, const ChainD&, double, const int64_t[2], const
                          int, size_t, size_t, int, float, unsigned, cudaStream_t);
 int launch_rectify_u8c3(cc_ctx*, const ChainD&, double, const int64_t[2], const uint8_t*, uint8_t*,
                         int, int, size_t, size_t, int, const uint8_t[3], unsigned, cudaStream_t);
+int launch_rectify_f32c1_views(cc_ctx*, const ChainD*, const double*, const int64_t*, int, const float*, float*, int, int,
+                               size_t, size_t, int, float, unsigned, cudaStream_t, bool*);
+int launch_rectify_u8c3_views(cc_ctx*, const ChainD*, const double*, const int64_t*, int, const uint8_t*, uint8_t*, int,
+                              int, size_t, size_t, int, const uint8_t[3], unsigned, cudaStream_t, bool*);
+int rectify_views_per_launch();
 int launch_rectify_map(cc_ctx*, const ChainD&, double, const int64_t[2], double*, double*, int, int,
                        size_t, cudaStream_t);
 int launch_rectify_map_f32(cc_ctx*, const ChainD&, double, const int64_t[2], float*, float*, int, int,
@@ -435,10 +441,11 @@ int cc_rectify_u8c3(cc_ctx* ctx, const cc_intr* intr, const cc_view* view, doubl
 // image with its own extrinsic (src/plot_calibration.jl:36-42).  frames [v * frames_per_view,
 // (v + 1) * frames_per_view) use views[v], ratios[v], axs_mins[2v .. 2v+1].  Every view is one
 // launch with its own cached tile plan.
-template <typename P, typename F>
+template <typename P, typename F, typename G>
 static int rectify_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views, int nviews, const double* ratios,
                          const int64_t* axs_mins, const P* src, P* dst, int sz1, int sz2, size_t pitch,
-                         size_t frame_stride, int frames_per_view, int channels, cudaStream_t stream, F launch) {
+                         size_t frame_stride, int frames_per_view, int channels, cudaStream_t stream, F launch,
+                         G launch_group) {
     CC_REQUIRE(ctx && intr && (nviews == 0 || (views && ratios && axs_mins)), "NULL argument");
     CC_REQUIRE(nviews >= 0 && frames_per_view >= 0, "bad counts");
     CC_REQUIRE((long long)nviews * frames_per_view <= 65535, "at most 65535 frames per call");
@@ -453,6 +460,23 @@ static int rectify_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views,
     CC_GUARD;
     if ((rc = enter(ctx))) return rc;
     if (nviews == 0 || frames_per_view == 0) return CC_OK;
+    // Groups of up to 64 views in ONE launch each (rectify.cu: launch_rectify_*_views) when the layout can be
+    // staged; CAMCAL_VIEWS_SINGLE=0 (tuning knob) or a group that cannot be staged: one launch per view, below.
+    std::vector<ChainD> chs((size_t)nviews);
+    for (int v = 0; v < nviews; ++v) build_chain(intr, views + v, &chs[v]);
+    std::vector<char> done((size_t)nviews, 0);
+    bool single = true;
+    if (const char* e = getenv("CAMCAL_VIEWS_SINGLE")) single = atoi(e) != 0;
+    int ndone = 0;
+    const int per = rectify_views_per_launch();
+    for (int v0 = 0; single && v0 < nviews; v0 += per) {
+        const int nv = std::min(per, nviews - v0);
+        const size_t off = (size_t)v0 * frames_per_view * frame_stride * channels;
+        bool ok = false;
+        if ((rc = launch_group(chs.data() + v0, ratios + v0, axs_mins + 2 * v0, nv, src + off, dst + off, stream, &ok))) return rc;
+        if (ok) { for (int v = v0; v < v0 + nv; ++v) done[v] = 1; ndone += nv; }
+    }
+    if (ndone == nviews) return CC_OK;
     // One launch per view.  On a single stream the launches serialise: every persistent kernel ramps up
     // and drains alone (a 1080p frame is ~15 us of launch + tail for ~5 us of work).  The views are
     // therefore spread round-robin over the context's side streams, forked from and joined to `stream`
@@ -468,11 +492,10 @@ static int rectify_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views,
         }
     }
     for (int v = 0; v < nviews; ++v) {
-        ChainD ch;
-        build_chain(intr, views + v, &ch);
+        if (done[v]) continue;
         const size_t off = (size_t)v * frames_per_view * frame_stride * channels;
         cudaStream_t st = lanes > 1 ? ctx->pipe_stream[v % lanes] : stream;
-        if ((rc = launch(ch, ratios[v], axs_mins + 2 * v, src + off, dst + off, st))) break;
+        if ((rc = launch(chs[v], ratios[v], axs_mins + 2 * v, src + off, dst + off, st))) break;
     }
     if (lanes > 1) {                                  // join even after an error: nothing stays forked
         for (int k = 0; k < lanes; ++k) {
@@ -497,6 +520,13 @@ int cc_rectify_f32c1_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* view
                          [&](const ChainD& ch, double ratio, const int64_t* axs, const float* s, float* d, cudaStream_t st) {
                              return launch_rectify_f32c1(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
                                                          frames_per_view, fill, flags, st);
+                         },
+                         [&](const ChainD* chs, const double* rs, const int64_t* axs, int nv, const float* s, float* d,
+                             cudaStream_t st, bool* ok) {
+                             *ok = false;
+                             if (flags & CC_GATHER_DIRECT) return (int)CC_OK;
+                             return launch_rectify_f32c1_views(ctx, chs, rs, axs, nv, s, d, sz1, sz2, pitch, frame_stride,
+                                                               frames_per_view, fill, flags, st, ok);
                          });
 }
 
@@ -510,6 +540,13 @@ int cc_rectify_u8c3_views(cc_ctx* ctx, const cc_intr* intr, const cc_view* views
                          [&](const ChainD& ch, double ratio, const int64_t* axs, const uint8_t* s, uint8_t* d, cudaStream_t st) {
                              return launch_rectify_u8c3(ctx, ch, ratio, axs, s, d, sz1, sz2, pitch, frame_stride,
                                                         frames_per_view, fill, flags, st);
+                         },
+                         [&](const ChainD* chs, const double* rs, const int64_t* axs, int nv, const uint8_t* s, uint8_t* d,
+                             cudaStream_t st, bool* ok) {
+                             *ok = false;
+                             if (flags & CC_GATHER_DIRECT) return (int)CC_OK;
+                             return launch_rectify_u8c3_views(ctx, chs, rs, axs, nv, s, d, sz1, sz2, pitch, frame_stride,
+                                                              frames_per_view, fill, flags, st, ok);
                          });
 }
 

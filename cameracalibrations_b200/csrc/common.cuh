@@ -69,6 +69,10 @@ struct cc_ctx {
     static const int NPLAN = 64;
     void* rect_plans[NPLAN];
     int rect_plan_next;
+    // tile plans of groups of views rectified in one launch (rectify.cu: MultiPlan), most recent NMULTI groups
+    static const int NMULTI = 4;
+    void* multi_plans[NMULTI];
+    int multi_plan_next;
     // ticket counters of the persistent rectification kernels (rectify.cu: RectSched)
     static const int NSCHED = 16;
     void* sched_pool;

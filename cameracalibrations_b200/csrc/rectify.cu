@@ -113,7 +113,18 @@ struct TileCfg {
     int fg;                // frames per group: the tile's map is built once per group and reused
     uint32_t widen_mul;    // f32c1 exact: 2^29, the multiplier of the integer float->double widening (a kernel
                            // parameter so that ptxas keeps ONE IMAD.WIDE instead of two shifts, rectify_f32c1.cuh)
+    // *_views_kernel only (frames with different views in ONE launch): units are (strip x, tile y, group) with
+    // group = view * gpv + frame group of the view; the tile headers / q2 terms of view v start at v * tiles / v * sz2
+    int fpv;               // frames per view
+    int gpv;               // frame groups per view
+    int tiles;             // strips * ntiles2
 };
+
+// Frames with different views in one launch (cc_rectify_*_views): what the single-view kernels take as
+// launch parameters, per view, in the kernel's parameter space (constant bank: a warp-uniform index).
+constexpr int kMaxViews = 64;
+struct ViewParams { RectExact pe; RectFast pf; RectGeom g; };
+struct ViewTable { ViewParams v[kMaxViews]; };
 
 // f32c1: per-tile header precomputed on the host (RectPlan), read straight from global memory
 struct __align__(16) TileHdr {
@@ -122,7 +133,7 @@ struct __align__(16) TileHdr {
     uint32_t R1, R2;       // number of valid local first-tap indices per axis (0: nothing staged)
     int x0, y0;            // box origin: TMA coordinates (x0: f32 texels / u8 BYTES of the line, multiple of 16 bytes; y0: lines; may be negative)
     uint32_t base_off;     // byte offset of local tap (0, 0) inside the stage (pixels are 4 or 3 bytes)
-    uint32_t pad;
+    uint32_t view;         // *_views_kernel: index of the unit's view, written by the producer (0 in the plan tables)
 };
 static_assert(sizeof(TileHdr) == 48, "TileHdr is read as three 16-byte words");
 
@@ -287,10 +298,16 @@ static void plan_free(RectPlan* p) {
     delete p;
 }
 
+static void multi_free(void* mp);
+
 void rectify_free_plans(cc_ctx* ctx) {
     for (int i = 0; i < cc_ctx::NPLAN; ++i) {
         plan_free(static_cast<RectPlan*>(ctx->rect_plans[i]));
         ctx->rect_plans[i] = nullptr;
+    }
+    for (int i = 0; i < cc_ctx::NMULTI; ++i) {
+        multi_free(ctx->multi_plans[i]);
+        ctx->multi_plans[i] = nullptr;
     }
 }
 
@@ -375,36 +392,49 @@ static void plan_footprints(RectPlan* p) {
 // LDS), with anything else whole groups of lanes collide (1.7 wavefronts with 192-byte lines).
 static int floor_to(int v, int m) { return v >= 0 ? (v / m) * m : -(((-v) + m - 1) / m) * m; }
 
-static void plan_boxes(RectPlan* p) {
-    const RectGeom& g = p->key.g;
-    const int pxb = p->key.pxb;
+// staged box of a footprint of need1 x need2 texels (tilt: RectPlan.tilt); box_bytes == 0: not worth staging
+struct BoxDims { int box1, box2, pitch_b, box_bytes; };
+
+static BoxDims box_dims(int need1, int need2, int tilt, int pxb) {
+    BoxDims d;
     if (pxb == 4) {
         const int unit = 4;
-        p->box1 = (p->need1 + unit - 1 + unit - 1) / unit * unit;      // + unit - 1: the origin is rounded down
+        d.box1 = (need1 + unit - 1 + unit - 1) / unit * unit;          // + unit - 1: the origin is rounded down
         const int align = CAMCAL_PITCH_ALIGN_F32;
-        p->pitch_b = (p->box1 * pxb + align - 1) / align * align;
-        p->box1 = p->pitch_b / pxb;                                    // usable pixels per line
+        d.pitch_b = (d.box1 * pxb + align - 1) / align * align;
+        d.box1 = d.pitch_b / pxb;                                      // usable pixels per line
     } else {
-        const int need_b = p->need1 * 3 + 15;                          // + 15: the byte origin is rounded down
+        const int need_b = need1 * 3 + 15;                             // + 15: the byte origin is rounded down
         int pitch = (need_b + 15) / 16 * 16;
 #if CAMCAL_PITCH_ALIGN_U8 == 0
-        const int want = p->tilt >= 0 ? 4 : 28;                        // pitch in words, mod 32
+        const int want = tilt >= 0 ? 4 : 28;                           // pitch in words, mod 32
+        const int dense = pitch;
         while ((pitch / 4) % 32 != want) pitch += 16;
+        // a TMA box line holds at most 256 elements (bytes here): a footprint whose bank-disjoint pitch does
+        // not fit keeps the dense pitch (some bank conflicts) rather than losing the staged path altogether
+        if (pitch > 256 && dense <= 256) pitch = dense;
 #else
         pitch = (pitch + CAMCAL_PITCH_ALIGN_U8 - 1) / CAMCAL_PITCH_ALIGN_U8 * CAMCAL_PITCH_ALIGN_U8;
 #endif
-        p->pitch_b = pitch;
-        p->box1 = pitch / 3;
+        d.pitch_b = pitch;
+        d.box1 = pitch / 3;
     }
-    p->box2 = p->need2;
-    while (((size_t)p->pitch_b * p->box2) % 128) ++p->box2;           // every stage base stays 128-byte aligned
-    const int box1_elems = (pxb == 4) ? p->pitch_b / 4 : p->pitch_b;
-    p->box_bytes = p->pitch_b * p->box2;
-    if (box1_elems > 256 || p->box2 > 256 || p->box_bytes > 40 * 1024) p->box_bytes = 0;   // not worth staging
-    if (!p->box_bytes) return;
-    p->hdr.resize((size_t)p->n1 * p->n2);
-    for (size_t t = 0; t < p->hdr.size(); ++t) {
-        TileHdr& h = p->hdr[t];
+    d.box2 = need2;
+    while (((size_t)d.pitch_b * d.box2) % 128) ++d.box2;              // every stage base stays 128-byte aligned
+    const int box1_elems = (pxb == 4) ? d.pitch_b / 4 : d.pitch_b;
+    d.box_bytes = d.pitch_b * d.box2;
+    if (box1_elems > 256 || d.box2 > 256 || d.box_bytes > 40 * 1024) d.box_bytes = 0;   // not worth staging
+    return d;
+}
+
+// tile headers of a plan's footprints for a staged box of the given size (the plan's own, or the common box of
+// a group of views: any box at least as large as the plan's footprint gives the same pixels)
+static void fill_headers(const RectPlan* p, const BoxDims& d, TileHdr* hdr) {
+    const RectGeom& g = p->key.g;
+    const int pxb = p->key.pxb;
+    const size_t ntiles = (size_t)p->n1 * p->n2;
+    for (size_t t = 0; t < ntiles; ++t) {
+        TileHdr& h = hdr[t];
         memset(&h, 0, sizeof(h));
         const int y0 = p->origin[2 * t + 1] - 2;
         // first tap g1 (0-based texel index): inside the box (both taps) and inside the frame
@@ -413,16 +443,16 @@ static void plan_boxes(RectPlan* p) {
             const int x0 = floor_to(p->origin[2 * t] - 2, 4);
             h.x0 = x0;
             g_lo = std::max(0, x0);
-            g_hi = std::min(x0 + p->box1 - 2, g.sz1 - 2);
+            g_hi = std::min(x0 + d.box1 - 2, g.sz1 - 2);
             h.base_off = (uint32_t)(g_lo - x0) * 4u;
         } else {
             const int xb0 = floor_to((p->origin[2 * t] - 2) * 3, 16);
             h.x0 = xb0;
             g_lo = std::max(0, xb0 >= 0 ? (xb0 + 2) / 3 : 0);                       // 3 g1 >= xb0
-            g_hi = std::min((xb0 + p->pitch_b - 6) >= 0 ? (xb0 + p->pitch_b - 6) / 3 : -1, g.sz1 - 2);   // 3 g1 + 6 <= xb0 + pitch
+            g_hi = std::min((xb0 + d.pitch_b - 6) >= 0 ? (xb0 + d.pitch_b - 6) / 3 : -1, g.sz1 - 2);   // 3 g1 + 6 <= xb0 + pitch
             h.base_off = (uint32_t)(3 * g_lo - xb0);
         }
-        const int lo2 = std::max(0, -y0), hi2 = std::min(p->box2 - 2, g.sz2 - 2 - y0);
+        const int lo2 = std::max(0, -y0), hi2 = std::min(d.box2 - 2, g.sz2 - 2 - y0);
         h.y0 = y0;
         h.R1 = p->p3_ok[t] ? (uint32_t)std::max(0, g_hi - g_lo + 1) : 0u;
         h.R2 = (uint32_t)std::max(0, hi2 - lo2 + 1);
@@ -431,12 +461,22 @@ static void plan_boxes(RectPlan* p) {
         h.Mk2 = 4503599627370496.0 - (double)k2;
         h.mk1 = 12582912.0f - (float)k1;
         h.mk2 = 12582912.0f - (float)k2;
-        h.base_off += (uint32_t)lo2 * (uint32_t)p->pitch_b;
+        h.base_off += (uint32_t)lo2 * (uint32_t)d.pitch_b;
     }
+}
+
+static void plan_boxes(RectPlan* p) {
+    const RectGeom& g = p->key.g;
+    const BoxDims d = box_dims(p->need1, p->need2, p->tilt, p->key.pxb);
+    p->box1 = d.box1; p->box2 = d.box2; p->pitch_b = d.pitch_b; p->box_bytes = d.box_bytes;
+    // the second-axis world terms do not depend on the box (the views call needs them for unstageable plans too)
     p->q2.resize((size_t)g.sz2);
     const double inv_ratio = 1.0 / p->key.ratio;
     for (int b = 0; b < g.sz2; ++b)       // rect_q2() of rectify_device.cuh, same two products
         p->q2[b] = ((double)((long long)g.axs1 + b) * inv_ratio) * p->key.ch.inv_cs;
+    if (!p->box_bytes) return;
+    p->hdr.resize((size_t)p->n1 * p->n2);
+    fill_headers(p, d, p->hdr.data());
 }
 
 // find or build the plan of this (calibration, geometry, tile shape); uploads on first use
@@ -540,7 +580,7 @@ static bool plan_tma(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom
 // raises it (a smaller plan must not lower the limit under a cached larger one, whichever context
 // of the process made either call).
 static std::mutex g_smem_mu;
-static size_t g_smem_attr[64][8];
+static size_t g_smem_attr[64][12];
 template <typename K>
 static int set_smem(cc_ctx* ctx, int kslot, K kernel, size_t bytes) {
     if (bytes <= 32 * 1024) return CC_OK;     // static smem (barriers + headers) counts against the 48 KB default too
@@ -585,8 +625,8 @@ void rectify_free_sched(cc_ctx* ctx) {
 }
 
 // persistent grid of a staged kernel: every CTA slot of the device (tickets do the balancing)
-template <typename K>
-static int persistent_grid(cc_ctx* ctx, int kslot, K kernel, size_t smem, const TileCfg& cfg, RectPlan* plan, bool exact,
+template <typename K, typename PL>
+static int persistent_grid(cc_ctx* ctx, int kslot, K kernel, size_t smem, const TileCfg& cfg, PL* plan, bool exact,
                            uint32_t* gsz) {
     // the occupancy query and the shared-memory attribute cost microseconds per call: once per plan
     int rc = set_smem(ctx, kslot, kernel, smem);
@@ -736,6 +776,227 @@ int launch_rectify_u8c3(cc_ctx* ctx, const ChainD& chd, double ratio, const int6
     CC_CUDA(cudaGetLastError());
     return CC_OK;
 }
+
+// --------------------------------------------------------------------------------------
+// Frames with different views in ONE launch (cc_rectify_*_views; the reference's plot loop,
+// src/plot_calibration.jl:36-42).  The views of a group share the frame layout, so they share the tensor map
+// and -- with the largest footprint of the group as the common staged box -- the ring; what differs per view
+// (coordinate parameters, axes, tile headers, q2 terms) is indexed by the unit's view.  One launch per view
+// (round 2's first version) spent more time in 64 ramp-ups, tails and host launches than in the work.
+// --------------------------------------------------------------------------------------
+struct MultiPlan {
+    std::vector<PlanKey> keys;     // the views of the group, in order
+    BoxDims d;                     // the common staged box
+    int n1, n2;
+    TileHdr* d_hdr;                // [view][tile]
+    double* d_q2;                  // [view][sz2]
+    int per_sm[2];
+    size_t per_sm_smem[2];
+};
+
+static void multi_free(void* p) {
+    MultiPlan* mp = static_cast<MultiPlan*>(p);
+    if (!mp) return;
+    if (mp->d_hdr) cudaFree(mp->d_hdr);
+    if (mp->d_q2) cudaFree(mp->d_q2);
+    delete mp;
+}
+
+static PlanKey plan_key(const ChainD& ch, double ratio, const RectGeom& g, int tw, int tl, int pxb) {
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
+    key.tw = tw; key.tl = tl; key.pxb = pxb;
+    return key;
+}
+
+// find or build the plan of a group of views; nullptr: not stageable (or out of memory) -- the caller falls
+// back to one launch per view
+static MultiPlan* multi_get(cc_ctx* ctx, const ChainD* chs, const double* ratios, const RectGeom* gs, int nviews,
+                            int tw, int tl, int pxb, cudaStream_t st) {
+    std::vector<PlanKey> keys((size_t)nviews);
+    for (int v = 0; v < nviews; ++v) keys[v] = plan_key(chs[v], ratios[v], gs[v], tw, tl, pxb);
+    for (int i = 0; i < cc_ctx::NMULTI; ++i) {
+        MultiPlan* mp = static_cast<MultiPlan*>(ctx->multi_plans[i]);
+        if (mp && mp->keys.size() == keys.size() && memcmp(mp->keys.data(), keys.data(), keys.size() * sizeof(PlanKey)) == 0)
+            return mp;
+    }
+    // footprints per view (cached RectPlans; copied at once: a later plan_get may evict an earlier plan)
+    std::vector<RectPlan> fp;
+    fp.reserve((size_t)nviews);
+    int need1 = 0, need2 = 0;
+    long long tilt = 0;
+    for (int v = 0; v < nviews; ++v) {
+        RectPlan* p = plan_get(ctx, chs[v], ratios[v], gs[v], tw, tl, pxb, st);
+        if (!p) return nullptr;
+        fp.push_back(*p);
+        need1 = std::max(need1, p->need1); need2 = std::max(need2, p->need2);
+        tilt += p->tilt;
+    }
+    MultiPlan* mp = new (std::nothrow) MultiPlan();
+    if (!mp) return nullptr;
+    mp->keys = keys;
+    mp->d = box_dims(need1, need2, tilt >= 0 ? 1 : -1, pxb);
+    mp->n1 = fp[0].n1; mp->n2 = fp[0].n2;
+    mp->d_hdr = nullptr; mp->d_q2 = nullptr;
+    mp->per_sm[0] = mp->per_sm[1] = 0; mp->per_sm_smem[0] = mp->per_sm_smem[1] = 0;
+    if (getenv("CAMCAL_DEBUG"))
+        fprintf(stderr, "[camcal] views: common footprint %d x %d -> box %d x %d pitch %d (%d B)\n", need1, need2, mp->d.box1,
+                mp->d.box2, mp->d.pitch_b, mp->d.box_bytes);
+    if (!mp->d.box_bytes) { delete mp; return nullptr; }
+    const size_t ntiles = (size_t)mp->n1 * mp->n2, sz2 = (size_t)gs[0].sz2;
+    std::vector<TileHdr> hdr(ntiles * nviews);
+    std::vector<double> q2(sz2 * nviews);
+    for (int v = 0; v < nviews; ++v) {
+        fill_headers(&fp[v], mp->d, hdr.data() + (size_t)v * ntiles);
+        memcpy(q2.data() + (size_t)v * sz2, fp[v].q2.data(), sz2 * sizeof(double));
+    }
+    const size_t hb = hdr.size() * sizeof(TileHdr), qb = q2.size() * sizeof(double);
+    if (cudaMalloc(&mp->d_hdr, hb) != cudaSuccess || cudaMalloc(&mp->d_q2, qb) != cudaSuccess ||
+        cudaMemcpyAsync(mp->d_hdr, hdr.data(), hb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(mp->d_q2, q2.data(), qb, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaGetLastError();
+        multi_free(mp);
+        return nullptr;
+    }
+    cudaStreamSynchronize(st);         // the host vectors go away; later calls may come on other streams
+    const int slot = ctx->multi_plan_next++ % cc_ctx::NMULTI;
+    if (ctx->multi_plans[slot]) {
+        cudaDeviceSynchronize();       // an evicted plan may still be read by a running kernel
+        multi_free(ctx->multi_plans[slot]);
+    }
+    ctx->multi_plans[slot] = mp;
+    return mp;
+}
+
+struct ViewsLaunch {
+    CUtensorMap tmap;
+    TileCfg cfg;
+    ViewTable vt;
+    RectGeom g;
+    MultiPlan* mp;
+};
+
+// tensor map, unit configuration and view table of one group; *ok = false: the single launch does not apply
+static int views_prepare(cc_ctx* ctx, const ChainD* chs, const double* ratios, const int64_t* axs_mins, int nviews,
+                         const void* src, int pxb, int tl, int sz1, int sz2, size_t pitch, size_t frame_stride, int fpv,
+                         int fg_max, cudaStream_t st, ViewsLaunch* L, bool* ok) {
+    *ok = false;
+    if (nviews < 1 || nviews > kMaxViews || fpv < 1) return CC_OK;
+    const int nframes = nviews * fpv;
+    const size_t pitch_b = pitch * pxb, frame_b = frame_stride * pxb;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) || (pitch_b & 15u) || (nframes > 1 && (frame_b & 15u))) return CC_OK;
+    EncodeTiledFn enc = encoder(ctx);
+    if (!enc) return CC_OK;
+    std::vector<RectGeom> gs((size_t)nviews);
+    for (int v = 0; v < nviews; ++v) gs[v] = make_geom(axs_mins + 2 * v, sz1, sz2, pitch, frame_stride, nframes);
+    MultiPlan* mp = multi_get(ctx, chs, ratios, gs.data(), nviews, kT, tl, pxb, st);
+    if (!mp) {
+        if (getenv("CAMCAL_DEBUG")) fprintf(stderr, "[camcal] views: group of %d not stageable (pxb %d)\n", nviews, pxb);
+        return CC_OK;
+    }
+    int stages = std::min(kMaxStages, std::max(2, CAMCAL_RING_BYTES / mp->d.box_bytes));
+    if (const char* e = getenv("CAMCAL_STAGES")) stages = std::min(kMaxStages, std::max(1, atoi(e)));   // tuning knob
+    while (stages > 2 && stages * mp->d.box_bytes > 56 * 1024) --stages;
+    memset(&L->tmap, 0, sizeof(L->tmap));
+    const int box1_elems = (pxb == 4) ? mp->d.pitch_b / 4 : mp->d.pitch_b;
+    cuuint64_t dims[3] = {(cuuint64_t)sz1 * (pxb == 4 ? 1 : 3), (cuuint64_t)sz2, (cuuint64_t)nframes};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch_b, (cuuint64_t)(nframes > 1 ? frame_b : pitch_b * sz2)};
+    cuuint32_t box[3] = {(cuuint32_t)box1_elems, (cuuint32_t)mp->d.box2, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&L->tmap, pxb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+            const_cast<void*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return CC_OK;
+    TileCfg& cfg = L->cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.box1 = mp->d.box1; cfg.box2 = mp->d.box2; cfg.pitch_b = mp->d.pitch_b; cfg.box_bytes = mp->d.box_bytes;
+    cfg.stages = stages;
+    cfg.strips = (sz1 + kT - 1) / kT;
+    cfg.ntiles2 = (sz2 + tl - 1) / tl;
+    cfg.tiles = cfg.strips * cfg.ntiles2;
+    // frames per group: as unit_cfg (keep ~8 units per resident CTA slot), within a view
+    const long long want = (long long)ctx->sm_count * 6 * 8;
+    int fg = std::min(fg_max, fpv);
+    while (fg > 1 && (long long)cfg.tiles * nviews * ((fpv + fg - 1) / fg) < want) fg = (fg + 1) / 2;
+    cfg.fg = fg;
+    cfg.fpv = fpv;
+    cfg.gpv = (fpv + fg - 1) / fg;
+    const long long units = (long long)cfg.tiles * nviews * cfg.gpv;
+    CC_REQUIRE(units < (1ll << 31), "too many tiles in one call: split the batch");
+    cfg.units = (uint32_t)units;
+    cfg.widen_mul = 0x20000000u;
+    for (int v = 0; v < nviews; ++v) {
+        L->vt.v[v].pe = make_exact(chs[v], ratios[v]);
+        L->vt.v[v].pf = make_fast(chs[v], ratios[v], gs[v]);
+        L->vt.v[v].g = gs[v];
+    }
+    for (int v = nviews; v < kMaxViews; ++v) L->vt.v[v] = L->vt.v[0];
+    L->g = gs[0];
+    L->mp = mp;
+    *ok = true;
+    return CC_OK;
+}
+
+int launch_rectify_f32c1_views(cc_ctx* ctx, const ChainD* chs, const double* ratios, const int64_t* axs_mins, int nviews,
+                               const float* src, float* dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
+                               int fpv, float fill, unsigned flags, cudaStream_t st, bool* ok) {
+    const bool exact = !(flags & CC_COORD_F32);
+    *ok = false;
+    ViewsLaunch L;                     // 15 KB: the view table goes to the kernel by value
+    ViewsLaunch* Lp = &L;
+    int rc = views_prepare(ctx, chs, ratios, axs_mins, nviews, src, 4, kTLf, sz1, sz2, pitch, frame_stride, fpv,
+                           exact ? kFGf32Exact : kFGf32Fast, st, Lp, ok);
+    if (rc || !*ok) return rc;
+    const size_t smem = (size_t)Lp->cfg.stages * Lp->cfg.box_bytes;
+    uint32_t gsz = 0;
+    rc = exact ? persistent_grid(ctx, 6, rectify_f32c1_views_kernel<true>, smem, Lp->cfg, Lp->mp, true, &gsz)
+               : persistent_grid(ctx, 7, rectify_f32c1_views_kernel<false>, smem, Lp->cfg, Lp->mp, false, &gsz);
+    RectSched* sched = nullptr;
+    if (!rc) rc = sched_acquire(ctx, st, &sched);
+    if (rc) return rc;
+    if (exact) rectify_f32c1_views_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(Lp->tmap, Lp->vt, Lp->g, Lp->cfg, Lp->mp->d_hdr, Lp->mp->d_q2, sched, src, dst, fill);
+    else       rectify_f32c1_views_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(Lp->tmap, Lp->vt, Lp->g, Lp->cfg, Lp->mp->d_hdr, Lp->mp->d_q2, sched, src, dst, fill);
+    sched_release(ctx, st);
+    ctx->launches++;
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int launch_rectify_u8c3_views(cc_ctx* ctx, const ChainD* chs, const double* ratios, const int64_t* axs_mins, int nviews,
+                              const uint8_t* src, uint8_t* dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
+                              int fpv, const uint8_t fill[3], unsigned flags, cudaStream_t st, bool* ok) {
+    const bool exact = !(flags & CC_COORD_F32);
+    *ok = false;
+    const int nframes = nviews * fpv;
+    // the staged kernel writes whole 32-bit words: 4-byte aligned output lines
+    const bool dst_ok = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0 && ((pitch * 3) & 3u) == 0 &&
+                        (nframes <= 1 || ((frame_stride * 3) & 3u) == 0);
+    if (!dst_ok) return CC_OK;
+    ViewsLaunch L;
+    ViewsLaunch* Lp = &L;
+    int rc = views_prepare(ctx, chs, ratios, axs_mins, nviews, src, 3, kTLu, sz1, sz2, pitch, frame_stride, fpv,
+                           exact ? kFGu8Exact : kFGu8Fast, st, Lp, ok);
+    if (rc || !*ok) return rc;
+    const uchar3 f = make_uchar3(fill[0], fill[1], fill[2]);
+    const unsigned frame_bytes = (unsigned)((pitch * (size_t)(sz2 - 1) + (size_t)sz1) * 3);
+    Lp->cfg.stages = std::max(2, Lp->cfg.stages / kU8FramesPerStage);
+    const size_t smem = (size_t)Lp->cfg.stages * kU8FramesPerStage * Lp->cfg.box_bytes + 16;
+    uint32_t gsz = 0;
+    rc = exact ? persistent_grid(ctx, 8, rectify_u8c3_views_kernel<true>, smem, Lp->cfg, Lp->mp, true, &gsz)
+               : persistent_grid(ctx, 9, rectify_u8c3_views_kernel<false>, smem, Lp->cfg, Lp->mp, false, &gsz);
+    RectSched* sched = nullptr;
+    if (!rc) rc = sched_acquire(ctx, st, &sched);
+    if (rc) return rc;
+    if (exact) rectify_u8c3_views_kernel<true><<<gsz, kConsumerThreads + 32, smem, st>>>(Lp->tmap, Lp->vt, Lp->g, Lp->cfg, Lp->mp->d_hdr, Lp->mp->d_q2, sched, src, dst, f, frame_bytes);
+    else       rectify_u8c3_views_kernel<false><<<gsz, kConsumerThreads + 32, smem, st>>>(Lp->tmap, Lp->vt, Lp->g, Lp->cfg, Lp->mp->d_hdr, Lp->mp->d_q2, sched, src, dst, f, frame_bytes);
+    sched_release(ctx, st);
+    ctx->launches++;
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+int rectify_views_per_launch() { return kMaxViews; }
 
 int launch_rectify_map(cc_ctx* ctx, const ChainD& chd, double ratio, const int64_t axs_min[2],
                        double* map_row, double* map_col, int sz1, int sz2, size_t pitch,

@@ -170,11 +170,14 @@ __device__ __forceinline__ double bilerp_scaled(double a00, double a10, double a
 #define CAMCAL_F32_MAXNREG_FAST 0
 #endif
 // the kernel body; NF = frames per ring stage (the two __global__ wrappers are below)
-template <bool EXACT, int NF>
-__device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, const RectExact& pe, const RectFast& pf,
+// VIEWS: frames with different views in one launch (cc_rectify_f32c1_views) -- coordinate parameters and axes of
+// the unit's view come from the view table in the kernel's parameter space (vt; index = TileHdr.view)
+template <bool EXACT, int NF, bool VIEWS = false>
+__device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, const RectExact& pe0, const RectFast& pf0,
                                                    const RectGeom& g, const TileCfg& cfg, const TileHdr* __restrict__ plan,
                                                    const double* __restrict__ q2tab, RectSched* __restrict__ sched,
-                                                   const float* __restrict__ src, float* __restrict__ dst, float fill) {
+                                                   const float* __restrict__ src, float* __restrict__ dst, float fill,
+                                                   const ViewTable* vt = nullptr) {
     constexpr int TL = kTLf;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
     static_assert(LPW % 2 == 0 && LPW <= 16, "pairs of lines; masks are 16 bits");
@@ -185,7 +188,7 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        producer_loop<EXACT, TL, 1, NF>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
+        producer_loop<EXACT, TL, 1, NF, VIEWS>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 
@@ -208,6 +211,7 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
     uint32_t phase = 0;
     int4 pos = make_int4(0, 0, 0, 0);
     int frames_left = 0, frame_z = 0;
+    [[maybe_unused]] uint32_t view = 0;
     float* o_cur = dst;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
@@ -226,6 +230,10 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
         } else {
             pos.w = 0;
         }
+        if (VIEWS && pos.w) view = __shfl_sync(0xffffffffu, ring.hdr[s].view, 0);
+        const RectExact& pe = VIEWS ? vt->v[view].pe : pe0;
+        const RectFast& pf = VIEWS ? vt->v[view].pf : pf0;
+        const RectGeom& gv = VIEWS ? vt->v[view].g : g;     // axs0 / axs1 of the view (everything else is the launch's)
         if (pos.w) {                                   // ---- first frame of a unit: build the map
             const TileHdr* h = &ring.hdr[s];
             const int a_w = pos.x * kT;
@@ -242,7 +250,7 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
                     if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
             }
             if (EXACT) {
-                const RowTermD rtd = rect_row_term(pe, g.axs0 + a_c);
+                const RowTermD rtd = rect_row_term(pe, gv.axs0 + a_c);
                 const double Mk1 = h->Mk1, Mk2 = h->Mk2;
                 const double* q2p = &ring.q2[s][warp * LPW];
 #pragma unroll
@@ -260,10 +268,10 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
                     else if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) m_fill |= 1u << e;   // rare: border tiles
                 }
             } else {
-                const RowTermF rtf = rect_row_term(pf, g.axs0 + a_c);
+                const RowTermF rtf = rect_row_term(pf, gv.axs0 + a_c);
                 const float mk1 = h->mk1, mk2 = h->mk2;
                 float2 ip;
-                ip.x = (float)(g.axs1 + b0) - pf.c2;
+                ip.x = (float)(gv.axs1 + b0) - pf.c2;
                 ip.y = ip.x + 1.0f;
 #pragma unroll
                 for (int hh = 0; hh < LPW / 2; ++hh) {
@@ -333,11 +341,11 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
                 if (m_gen) {
                     RowTermD rtd;
                     RowTermF rtf;
-                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+                    if (EXACT) rtd = rect_row_term(pe, gv.axs0 + a); else rtf = rect_row_term(pf, gv.axs0 + a);
 #pragma unroll 1
                     for (int e = 0; e < LPW; ++e)
                         if ((m_gen >> e) & 1u)
-                            __stcs(o + (long long)e * pitch, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b0 + e, fill));
+                            __stcs(o + (long long)e * pitch, sample_direct_f32<EXACT>(pe, pf, rtd, rtf, gv, sframe, pitch, b0 + e, fill));
                 }
             } else {
 #pragma unroll 1
@@ -365,8 +373,8 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
                 } else {
                     RowTermD rtd;
                     RowTermF rtf;
-                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
-                    v = sample_direct_f32<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch, b0 + e, fill);
+                    if (EXACT) rtd = rect_row_term(pe, gv.axs0 + a); else rtf = rect_row_term(pf, gv.axs0 + a);
+                    v = sample_direct_f32<EXACT>(pe, pf, rtd, rtf, gv, sframe, pitch, b0 + e, fill);
                 }
                 __stcs(o, v);
             }
@@ -504,6 +512,17 @@ rectify_f32c1_single_kernel(const __grid_constant__ CUtensorMap tmap, const __gr
                             const double* __restrict__ q2tab, RectSched* __restrict__ sched,
                             const float* __restrict__ src, float* __restrict__ dst, float fill) {
     rectify_f32c1_body<EXACT, 1>(tmap, pe, pf, g, cfg, plan, q2tab, sched, src, dst, fill);
+}
+
+// frames with different views in one launch, one frame per stage (cc_rectify_f32c1_views)
+template <bool EXACT>
+__global__ void CAMCAL_F32_KERNEL_ATTR(EXACT)
+rectify_f32c1_views_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ViewTable vt,
+                           const __grid_constant__ RectGeom g, const __grid_constant__ TileCfg cfg,
+                           const TileHdr* __restrict__ plan, const double* __restrict__ q2tab,
+                           RectSched* __restrict__ sched, const float* __restrict__ src, float* __restrict__ dst,
+                           float fill) {
+    rectify_f32c1_body<EXACT, 1, true>(tmap, vt.v[0].pe, vt.v[0].pf, g, cfg, plan, q2tab, sched, src, dst, fill, &vt);
 }
 
 }  // namespace cc

@@ -64,7 +64,9 @@ __device__ __forceinline__ uint32_t take_ticket(RectSched* sched, int lane_id) {
 // consumers read the slot on a unit's first frame only (CAMCAL_POS_TRACK) and count the frames down.
 // NF: frames per ring stage (2: a stage holds the boxes of two consecutive frames of the unit -- one at
 // the odd end of a unit -- so the consumers pay one hand-over per pair)
-template <bool EXACT, int TL, int PXB, int NF = 1>
+// VIEWS: frames with different views in one launch -- the third unit coordinate counts (view, frame group of
+// the view), the view's tables start at view * tiles / view * sz2, and the view index travels in the header.
+template <bool EXACT, int TL, int PXB, int NF = 1, bool VIEWS = false>
 __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const RectGeom& g, const TileCfg& cfg,
                                               const TileHdr* __restrict__ plan,
                                               const double* __restrict__ q2tab, RectSched* sched,
@@ -81,16 +83,28 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* tmap, const Rec
         const int x = (int)(u % (uint32_t)cfg.strips);
         const uint32_t r = u / (uint32_t)cfg.strips;
         const int y = (int)(r % (uint32_t)cfg.ntiles2);
-        const int f0 = (int)(r / (uint32_t)cfg.ntiles2) * cfg.fg;
-        const int f1 = min(f0 + cfg.fg, g.nframes);
-        const uint32_t* hp = reinterpret_cast<const uint32_t*>(plan + x * cfg.ntiles2 + y);
+        int f0 = (int)(r / (uint32_t)cfg.ntiles2) * cfg.fg;
+        int f1 = min(f0 + cfg.fg, g.nframes);
+        const TileHdr* hdr_v = plan;
+        const double* q2_v = q2tab;
+        [[maybe_unused]] uint32_t view = 0;
+        if (VIEWS) {
+            const uint32_t grp = r / (uint32_t)cfg.ntiles2;
+            view = grp / (uint32_t)cfg.gpv;
+            f0 = (int)view * cfg.fpv + (int)(grp - view * (uint32_t)cfg.gpv) * cfg.fg;
+            f1 = min(f0 + cfg.fg, ((int)view + 1) * cfg.fpv);
+            hdr_v = plan + (size_t)view * cfg.tiles;
+            q2_v = q2tab + (size_t)view * g.sz2;
+        }
+        const uint32_t* hp = reinterpret_cast<const uint32_t*>(hdr_v + x * cfg.ntiles2 + y);
         uint32_t hword = 0;
         if (lane_id < 12) hword = __ldg(hp + lane_id);            // the 48-byte header, one word per lane
+        if (VIEWS && lane_id == 11) hword = view;
         [[maybe_unused]] double q2a = 0, q2b = 0;
         if (EXACT) {
             const int b = y * TL + lane_id;
-            q2a = __ldg(q2tab + min(b, g.sz2 - 1));
-            if (TL > 32) q2b = __ldg(q2tab + min(b + 32, g.sz2 - 1));
+            q2a = __ldg(q2_v + min(b, g.sz2 - 1));
+            if (TL > 32) q2b = __ldg(q2_v + min(b + 32, g.sz2 - 1));
         }
         u_next = take_ticket(sched, lane_id);
         const int x0 = __shfl_sync(0xffffffffu, (int)hword, 8), y0 = __shfl_sync(0xffffffffu, (int)hword, 9);

@@ -415,18 +415,15 @@ __device__ __noinline__ uint32_t reblend_exact_u8(const RectExact* pe, const Rec
 #ifndef CAMCAL_U8_MAXNREG_FAST
 #define CAMCAL_U8_MAXNREG_FAST 0
 #endif
-template <bool EXACT>
-#if CAMCAL_U8_MAXNREG_FAST > 0
-__global__ void __launch_bounds__(kConsumerThreads + 32) __maxnreg__(EXACT ? 65536 / ((kConsumerThreads + 32) * kMinBlocksU8Exact) / 8 * 8 : CAMCAL_U8_MAXNREG_FAST)
-#else
-__global__ void __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksU8Exact : kMinBlocksU8)
-#endif
-rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
-                    const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
-                    const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
-                    const double* __restrict__ q2tab, RectSched* __restrict__ sched,
-                    const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
-                    unsigned frame_bytes) {
+// the kernel body (the __global__ wrappers are below).  VIEWS: frames with different views in one launch
+// (cc_rectify_u8c3_views) -- coordinate parameters and axes of the unit's view come from the view table in the
+// kernel's parameter space (vt; index = TileHdr.view)
+template <bool EXACT, bool VIEWS>
+__device__ __forceinline__ void rectify_u8c3_body(const CUtensorMap& tmap, const RectExact& pe0, const RectFast& pf0,
+                                                  const RectGeom& g, const TileCfg& cfg, const TileHdr* __restrict__ plan,
+                                                  const double* __restrict__ q2tab, RectSched* __restrict__ sched,
+                                                  const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
+                                                  unsigned frame_bytes, const ViewTable* vt) {
     constexpr int TL = kTLu;                      // lines per tile
     constexpr int LPW = TL / kWarps;              // lines per warp per tile = pixels per lane
     constexpr int NP = LPW / 2;                   // pairs of lines
@@ -440,7 +437,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     ring_init(&ring, cfg.stages);
 
     if (warp == kWarps) {                              // ---- producer warp
-        producer_loop<EXACT, TL, 1, kU8FramesPerStage>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
+        producer_loop<EXACT, TL, 1, kU8FramesPerStage, VIEWS>(&tmap, g, cfg, plan, q2tab, sched, &ring, stage_mem, lane_id);
         return;
     }
 
@@ -468,6 +465,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     uint32_t phase = 0;
     int4 pos = make_int4(0, 0, 0, 0);
     int frames_left = 0, frame_z = 0;
+    [[maybe_unused]] uint32_t view = 0;
     for (;;) {
         mbar_wait(&ring.full[s], phase);
         // CAMCAL_POS_TRACK: the slot is read on a unit's first frame only; frame index and frames left
@@ -485,6 +483,10 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         } else {
             pos.w = 0;
         }
+        if (VIEWS && pos.w) view = __shfl_sync(0xffffffffu, ring.hdr[s].view, 0);
+        const RectExact& pe = VIEWS ? vt->v[view].pe : pe0;
+        const RectFast& pf = VIEWS ? vt->v[view].pf : pf0;
+        const RectGeom& gv = VIEWS ? vt->v[view].g : g;     // axs0 / axs1 of the view (everything else is the launch's)
         if (pos.w) {                                   // ---- first frame of a unit: build the map
             const TileHdr* h = &ring.hdr[s];
             const int a_w = pos.x * kT;
@@ -501,7 +503,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
             }
             if (EXACT) {
-                const RowTermD rtd = rect_row_term(pe, g.axs0 + a_c);
+                const RowTermD rtd = rect_row_term(pe, gv.axs0 + a_c);
                 const double Mk1 = h->Mk1, Mk2 = h->Mk2;
                 const double* q2p = &ring.q2[s][warp * LPW];
                 const double up = 1.2676506002282294e30;      // 2^100
@@ -525,10 +527,10 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     else if (!(lin_ok(row, g.sz1) & lin_ok(col, g.sz2))) m_fill |= 1u << e;   // rare: border tiles
                 }
             } else {
-                const RowTermF rtf = rect_row_term(pf, g.axs0 + a_c);
+                const RowTermF rtf = rect_row_term(pf, gv.axs0 + a_c);
                 const float mk1 = h->mk1, mk2 = h->mk2;
                 float2 ip;
-                ip.x = (float)(g.axs1 + b0) - pf.c2;
+                ip.x = (float)(gv.axs1 + b0) - pf.c2;
                 ip.y = ip.x + 1.0f;
 #pragma unroll
                 for (int hh = 0; hh < NP; ++hh) {
@@ -636,7 +638,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                             if ((j ? dm[hh].y : dm[hh].x) > kCertThr) {
                                 const uint32_t bo = rel[e] + (kU8Bytes ? 0u : (selv[e] & 3u));
                                 store_rgb(oline + (long long)e * pitch3 + lane_id * 3,
-                                          reblend_exact_u8(&pe, &g, a, b0 + e, sbase + bo, sbase1 + bo));
+                                          reblend_exact_u8(&pe, &gv, a, b0 + e, sbase + bo, sbase1 + bo));
                             }
                         }
                     }
@@ -667,7 +669,7 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     blend_px2<EXACT>(t, t, bc2(f00), bc2(f10), bc2(f01), bc2(f11), v, vq, dm1);
                     if (EXACT && dm1.x > kCertThr) {
                         const uint32_t bo = rel[e] + (kU8Bytes ? 0u : (sel & 3u));
-                        v = reblend_exact_u8(&pe, &g, a, b0 + e, sbase + bo, sbase1 + bo);
+                        v = reblend_exact_u8(&pe, &gv, a, b0 + e, sbase + bo, sbase1 + bo);
                     }
                     store_rgb(o, v);
                 } else if (m_fill & bit) {
@@ -678,12 +680,12 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             if (m_gen) {
                 RowTermD rtd;
                 RowTermF rtf;
-                if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
+                if (EXACT) rtd = rect_row_term(pe, gv.axs0 + a); else rtf = rect_row_term(pf, gv.axs0 + a);
                 uint8_t* og = oline + lane_id * 3;
 #pragma unroll 1
                 for (int e = 0; e < LPW; ++e, og += pitch3)
                     if ((m_gen >> e) & 1u)
-                        store_rgb(og, sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b0 + e, fill));
+                        store_rgb(og, sample_direct_u8<EXACT>(pe, pf, rtd, rtf, gv, sframe, pitch3, frame_bytes, b0 + e, fill));
             }
         } else {
             // border tiles: per-pixel class, byte stores
@@ -714,15 +716,15 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     blend_px2<EXACT>(t, t, bc2(f00), bc2(f10), bc2(f01), bc2(f11), v, vq, dm1);
                     if (EXACT && dm1.x > kCertThr) {
                         const uint32_t bo = r + (kU8Bytes ? 0u : (sel & 3u));
-                        v = reblend_exact_u8(&pe, &g, a, b0 + e, sbase + bo, sbase1 + bo);
+                        v = reblend_exact_u8(&pe, &gv, a, b0 + e, sbase + bo, sbase1 + bo);
                     }
                 } else if ((m_fill >> e) & 1u) {
                     v = fill;
                 } else {
                     RowTermD rtd;
                     RowTermF rtf;
-                    if (EXACT) rtd = rect_row_term(pe, g.axs0 + a); else rtf = rect_row_term(pf, g.axs0 + a);
-                    v = sample_direct_u8<EXACT>(pe, pf, rtd, rtf, g, sframe, pitch3, frame_bytes, b0 + e, fill);
+                    if (EXACT) rtd = rect_row_term(pe, gv.axs0 + a); else rtf = rect_row_term(pf, gv.axs0 + a);
+                    v = sample_direct_u8<EXACT>(pe, pf, rtd, rtf, gv, sframe, pitch3, frame_bytes, b0 + e, fill);
                 }
                 store_rgb(o, v);
             }
@@ -733,6 +735,32 @@ rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         if (kPosTrack) { frames_left = max(frames_left - NF, 0); frame_z += NF; }
         if (++s == cfg.stages) { s = 0; phase ^= 1; }
     }
+}
+
+#if CAMCAL_U8_MAXNREG_FAST > 0
+#define CAMCAL_U8_KERNEL_ATTR(EXACT) __launch_bounds__(kConsumerThreads + 32) __maxnreg__(EXACT ? 65536 / ((kConsumerThreads + 32) * kMinBlocksU8Exact) / 8 * 8 : CAMCAL_U8_MAXNREG_FAST)
+#else
+#define CAMCAL_U8_KERNEL_ATTR(EXACT) __launch_bounds__(kConsumerThreads + 32, EXACT ? kMinBlocksU8Exact : kMinBlocksU8)
+#endif
+template <bool EXACT>
+__global__ void CAMCAL_U8_KERNEL_ATTR(EXACT)
+rectify_u8c3_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ RectExact pe,
+                    const __grid_constant__ RectFast pf, const __grid_constant__ RectGeom g,
+                    const __grid_constant__ TileCfg cfg, const TileHdr* __restrict__ plan,
+                    const double* __restrict__ q2tab, RectSched* __restrict__ sched,
+                    const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uchar3 fill3,
+                    unsigned frame_bytes) {
+    rectify_u8c3_body<EXACT, false>(tmap, pe, pf, g, cfg, plan, q2tab, sched, src, dst, fill3, frame_bytes, nullptr);
+}
+// frames with different views in one launch (cc_rectify_u8c3_views)
+template <bool EXACT>
+__global__ void CAMCAL_U8_KERNEL_ATTR(EXACT)
+rectify_u8c3_views_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ViewTable vt,
+                          const __grid_constant__ RectGeom g, const __grid_constant__ TileCfg cfg,
+                          const TileHdr* __restrict__ plan, const double* __restrict__ q2tab,
+                          RectSched* __restrict__ sched, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                          uchar3 fill3, unsigned frame_bytes) {
+    rectify_u8c3_body<EXACT, true>(tmap, vt.v[0].pe, vt.v[0].pf, g, cfg, plan, q2tab, sched, src, dst, fill3, frame_bytes, &vt);
 }
 
 }  // namespace cc

@@ -411,6 +411,55 @@ def test_rectify_views_is_the_plot_loop(cc, example_fit):
         cc.warp_views(c, [0, 1, 2, 3], _dev(frames[:6]), ratios[:4], axss[:4])            # 6 frames, 4 views
 
 
+def _perturbed_views(n):
+    return [((BENCH_VIEW[0][0] + 0.004 * i, BENCH_VIEW[0][1] - 0.003 * i, BENCH_VIEW[0][2] + 0.002 * i),
+             (BENCH_VIEW[1][0] + 0.03 * i, BENCH_VIEW[1][1] - 0.02 * i, BENCH_VIEW[1][2] + 0.1 * i)) for i in range(n)]
+
+
+@pytest.mark.parametrize("nv,k,sz", [(5, 1, (384, 200)), (3, 5, (256, 131)), (70, 2, (128, 96))])
+def test_rectify_views_one_launch_per_group(cc, nv, k, sz):
+    """cc_rectify_*_views rectifies groups of up to 64 views in ONE launch (rectify_*_views_kernel: view
+    table in the kernel's parameter space, common staged box, per-view tile headers).  Bit-equal to one
+    launch per view (CAMCAL_VIEWS_SINGLE=0) in all four variants, and to the oracle for the exact ones;
+    70 views = a group of 64 and a group of 6; k frames per view share the view's map."""
+    import os
+    intr = camera_for(sz)
+    views = _perturbed_views(nv)
+    c = _calib(cc, intr, views)
+    rng = np.random.default_rng(100 + nv)
+    frames = rng.random((nv * k, sz[1], sz[0]), dtype=np.float32)
+    f8 = rng.integers(0, 256, (nv * k, sz[1], sz[0], 3), dtype=np.uint8)
+    ratios, axss = [], []
+    for vi in range(nv):
+        _, _, ratio, axs = _rect_case(intr, sz, ratio_scale=1.0 + 0.01 * (vi % 5), view=views[vi])
+        ratios.append(ratio); axss.append(axs)
+    idx = list(range(nv))
+    dfr, df8 = _dev(frames), _dev(f8)
+    got = {}
+    ctx = cc.context(0)
+    for single in ("1", "0"):
+        os.environ["CAMCAL_VIEWS_SINGLE"] = single
+        try:
+            for coord in ("f64", "f32"):
+                n0 = ctx.launch_count()
+                got[(single, coord, "f")] = cc.warp_views(c, idx, dfr, ratios, axss, fill=-2.0, coord=coord).cpu().numpy()
+                got[(single, coord, "u")] = cc.warp_views(c, idx, df8, ratios, axss, fill=(3, 2, 1), coord=coord).cpu().numpy()
+                # one launch per group of <= 64 views and pixel format, against one per view
+                assert ctx.launch_count() - n0 == (2 * ((nv + 63) // 64) if single == "1" else 2 * nv), (single, coord)
+        finally:
+            os.environ.pop("CAMCAL_VIEWS_SINGLE", None)
+    for coord in ("f64", "f32"):
+        for px in ("f", "u"):
+            assert np.array_equal(got[("1", coord, px)], got[("0", coord, px)]), (coord, px)
+    for vi in sorted(set([0, nv // 2, nv - 1])):
+        ch = oc.chain(intr, *views[vi])
+        sl = slice(vi * k, (vi + 1) * k)
+        ref = oc.rectify_f32c1(ch, 1.0 / ratios[vi], axss[vi], frames[sl], fill=-2.0)
+        assert np.array_equal(got[("1", "f64", "f")][sl], ref), vi
+        assert (ref != -2.0).mean() > 0.5
+        assert np.array_equal(got[("1", "f64", "u")][sl], oc.rectify_u8c3(ch, 1.0 / ratios[vi], axss[vi], f8[sl], fill=(3, 2, 1))), vi
+
+
 def test_rectify_bounds_checked_build(cc):
     """The rectification parity tests once more against libcamcal_b200_chk.so, the build of the same
     sources with -DCAMCAL_CHECK_BOUNDS: every shared-memory tap address of the staged kernels is
@@ -427,7 +476,7 @@ def test_rectify_bounds_checked_build(cc):
         pytest.skip("already running against a variant library")
     env = dict(os.environ, CAMCAL_B200_LIB=lib)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
-                        "-k", "bit_exact or tilted or horizon or views_is or alternating or strided"],
+                        "-k", "bit_exact or tilted or horizon or views_is or views_one_launch or alternating or strided"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
