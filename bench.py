@@ -481,6 +481,22 @@ def extras(cc, torch, dev, c2cal, args):
             "note": "64 frames, 64 different views, one call = ONE launch (rectify_f32c1_views_kernel; tile plans cached after the first call); "
                     "first_call_ms includes building and uploading the 64 tile plans on the host"}
     del src, dst
+    # the same loop on what the reference's plot actually warps: RGB{N0f8} images, here 16 views x 4K u8 RGB
+    wl3 = WORKLOADS["c3"]
+    sz3 = wl3["sz"]
+    v16 = vlist[:16]
+    cal3 = cc.Calibration(wl3["intr"][:4], v16, 1.0, wl3["intr"][4], [f"{i}.png" for i in range(16)])
+    ratio3 = cc.get_ratio(geometry(wl3), 1.0)
+    axs3 = cc.get_axes(ratio3, 1.0, N_CORNERS, sz3)
+    src3 = torch.randint(0, 256, (16, sz3[1], sz3[0], 3), dtype=torch.uint8, device=dev)
+    dst3 = torch.empty_like(src3)
+    for coord in ("f64", "f32"):
+        ms = _time_ms(torch, lambda: cc.warp_views(cal3, list(range(16)), src3, [ratio3] * 16, [axs3] * 16, coord=coord, out=dst3), 10)
+        npx = 16 * sz3[0] * sz3[1]
+        ex[f"rectify_views_16x4k_u8_{coord}"] = {
+            "mpix_per_s": npx / (ms * 1e-3) / 1e6, "ms": ms, "hbm_frac": 6 * npx / (ms * 1e-3) / 1e9 / peak,
+            "note": "16 u8 RGB 4K frames, 16 different views, one call = one launch (rectify_u8c3_views_kernel)"}
+    del src3, dst3
     # ingest: compressed JPEG bytes -> device frames -> the views call, nothing returns to
     # the host in between (the reference: FileIO.load + warp per file, src/plot_calibration.jl:36-42)
     try:

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "rectify_device.cuh"
@@ -479,41 +480,72 @@ static void plan_boxes(RectPlan* p) {
     fill_headers(p, d, p->hdr.data());
 }
 
-// find or build the plan of this (calibration, geometry, tile shape); uploads on first use
-static RectPlan* plan_get(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom& g, int tw, int tl,
-                          int pxb, cudaStream_t st) {
-    PlanKey key;
-    memset(&key, 0, sizeof(key));
-    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
-    key.tw = tw; key.tl = tl; key.pxb = pxb;
+// tile headers and q2 terms of a plan to the device (once); false: out of device memory
+static bool plan_upload(RectPlan* p, cudaStream_t st) {
+    if (p->d_hdr || p->hdr.empty()) return true;
+    const size_t hb = p->hdr.size() * sizeof(TileHdr), qb = p->q2.size() * sizeof(double);
+    if (cudaMalloc(&p->d_hdr, hb) != cudaSuccess || cudaMalloc(&p->d_q2, qb) != cudaSuccess ||
+        cudaMemcpyAsync(p->d_hdr, p->hdr.data(), hb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(p->d_q2, p->q2.data(), qb, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaGetLastError();
+        if (p->d_hdr) cudaFree(p->d_hdr);
+        if (p->d_q2) cudaFree(p->d_q2);
+        p->d_hdr = nullptr; p->d_q2 = nullptr;
+        return false;
+    }
+    // later calls may come on other streams: make the tables visible to all of them
+    cudaStreamSynchronize(st);
+    return true;
+}
+
+static RectPlan* plan_find(cc_ctx* ctx, const PlanKey& key) {
     for (int i = 0; i < cc_ctx::NPLAN; ++i) {
         RectPlan* p = static_cast<RectPlan*>(ctx->rect_plans[i]);
         if (p && memcmp(&p->key, &key, sizeof(key)) == 0) return p;
     }
+    return nullptr;
+}
+
+// footprints, box and headers of one parameter set: host arithmetic only (safe to run on several threads)
+static RectPlan* plan_build(const PlanKey& key) {
     RectPlan* p = new (std::nothrow) RectPlan();
     if (!p) return nullptr;
     p->key = key; p->d_hdr = nullptr; p->d_q2 = nullptr;
     p->per_sm[0] = p->per_sm[1] = 0; p->per_sm_smem[0] = p->per_sm_smem[1] = 0;
     plan_footprints(p);
     plan_boxes(p);
-    if (!p->hdr.empty()) {
-        const size_t hb = p->hdr.size() * sizeof(TileHdr), qb = p->q2.size() * sizeof(double);
-        if (cudaMalloc(&p->d_hdr, hb) != cudaSuccess || cudaMalloc(&p->d_q2, qb) != cudaSuccess ||
-            cudaMemcpyAsync(p->d_hdr, p->hdr.data(), hb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemcpyAsync(p->d_q2, p->q2.data(), qb, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-            cudaGetLastError();
-            plan_free(p);
-            return nullptr;
-        }
-        // later calls may come on other streams: make the tables visible to all of them
-        cudaStreamSynchronize(st);
-    }
+    return p;
+}
+
+static void plan_insert(cc_ctx* ctx, RectPlan* p) {
     const int slot = ctx->rect_plan_next++ % cc_ctx::NPLAN;
     if (ctx->rect_plans[slot]) {
         cudaDeviceSynchronize();       // an evicted plan may still be read by a running kernel
         plan_free(static_cast<RectPlan*>(ctx->rect_plans[slot]));
     }
     ctx->rect_plans[slot] = p;
+}
+
+static PlanKey plan_key(const ChainD& ch, double ratio, const RectGeom& g, int tw, int tl, int pxb) {
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
+    key.tw = tw; key.tl = tl; key.pxb = pxb;
+    return key;
+}
+
+// find or build the plan of this (calibration, geometry, tile shape); its tables go to the device on first use
+static RectPlan* plan_get(cc_ctx* ctx, const ChainD& ch, double ratio, const RectGeom& g, int tw, int tl,
+                          int pxb, cudaStream_t st) {
+    const PlanKey key = plan_key(ch, ratio, g, tw, tl, pxb);
+    if (RectPlan* p = plan_find(ctx, key)) return plan_upload(p, st) ? p : nullptr;
+    RectPlan* p = plan_build(key);
+    if (!p) return nullptr;
+    if (!plan_upload(p, st)) {
+        plan_free(p);
+        return nullptr;
+    }
+    plan_insert(ctx, p);
     return p;
 }
 
@@ -802,14 +834,6 @@ static void multi_free(void* p) {
     delete mp;
 }
 
-static PlanKey plan_key(const ChainD& ch, double ratio, const RectGeom& g, int tw, int tl, int pxb) {
-    PlanKey key;
-    memset(&key, 0, sizeof(key));
-    key.ch = ch; key.ratio = ratio; key.g = g; key.g.nframes = 0; key.g.frame_stride = 0;
-    key.tw = tw; key.tl = tl; key.pxb = pxb;
-    return key;
-}
-
 // find or build the plan of a group of views; nullptr: not stageable (or out of memory) -- the caller falls
 // back to one launch per view
 static MultiPlan* multi_get(cc_ctx* ctx, const ChainD* chs, const double* ratios, const RectGeom* gs, int nviews,
@@ -821,18 +845,41 @@ static MultiPlan* multi_get(cc_ctx* ctx, const ChainD* chs, const double* ratios
         if (mp && mp->keys.size() == keys.size() && memcmp(mp->keys.data(), keys.data(), keys.size() * sizeof(PlanKey)) == 0)
             return mp;
     }
-    // footprints per view (cached RectPlans; copied at once: a later plan_get may evict an earlier plan)
+    // footprints per view: the cached RectPlans, the missing ones built on up to 16 host threads (the plot loop
+    // is a one-shot call: 64 cold views cost 64 x ~0.5 ms of host arithmetic on one thread) and cached without
+    // their device tables (the group uploads its own).  Copied at once: inserting may evict an earlier plan.
+    std::vector<RectPlan*> pl((size_t)nviews, nullptr);
+    std::vector<int> missing;
+    for (int v = 0; v < nviews; ++v) {
+        pl[v] = plan_find(ctx, keys[v]);
+        bool dup = false;                                  // the same view twice: build it once
+        for (int w = 0; w < v && !pl[v] && !dup; ++w) dup = memcmp(&keys[w], &keys[v], sizeof(PlanKey)) == 0;
+        if (!pl[v] && !dup) missing.push_back(v);
+    }
+    if (!missing.empty()) {
+        const int nt = (int)std::min<size_t>(missing.size(), std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+        std::vector<std::thread> th;
+        auto work = [&](int t) { for (size_t i = (size_t)t; i < missing.size(); i += (size_t)nt) pl[missing[i]] = plan_build(keys[missing[i]]); };
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
     std::vector<RectPlan> fp;
     fp.reserve((size_t)nviews);
     int need1 = 0, need2 = 0;
     long long tilt = 0;
+    bool oom = false;
     for (int v = 0; v < nviews; ++v) {
-        RectPlan* p = plan_get(ctx, chs[v], ratios[v], gs[v], tw, tl, pxb, st);
-        if (!p) return nullptr;
-        fp.push_back(*p);
-        need1 = std::max(need1, p->need1); need2 = std::max(need2, p->need2);
-        tilt += p->tilt;
+        if (!pl[v])                                        // a duplicate of an earlier view (or out of memory)
+            for (int w = 0; w < v && !pl[v]; ++w)
+                if (memcmp(&keys[w], &keys[v], sizeof(PlanKey)) == 0) pl[v] = pl[w];
+        if (!pl[v]) { oom = true; continue; }
+        fp.push_back(*pl[v]);
+        need1 = std::max(need1, pl[v]->need1); need2 = std::max(need2, pl[v]->need2);
+        tilt += pl[v]->tilt;
     }
+    for (int v : missing) if (pl[v]) plan_insert(ctx, pl[v]);
+    if (oom) return nullptr;
     MultiPlan* mp = new (std::nothrow) MultiPlan();
     if (!mp) return nullptr;
     mp->keys = keys;

@@ -36,6 +36,26 @@ if a.what in ("rectify", "all", "c2", "c3"):
                 cc.warp(cal, 0, src, ratio, axs, coord=coord, gather=a.gather, out=dst)
         torch.cuda.synchronize()
         del src, dst
+if a.what in ("views", "all"):
+    # frames with different views in one launch (rectify_*_views_kernel): 64 x 1080p fp32, 16 x 4K u8 RGB
+    BV = bench.BENCH_VIEW
+    vlist = [((BV[0][0] + 0.002 * i, BV[0][1], BV[0][2] + 0.001 * i), (BV[1][0] + 0.01 * i, BV[1][1], BV[1][2] + 0.05 * i)) for i in range(64)]
+    for wname, nv in (("c2", 64), ("c3", 16)):
+        wl = bench.WORKLOADS[wname]
+        sz = wl["sz"]
+        cal = cc.Calibration(wl["intr"][:4], vlist[:nv], 1.0, wl["intr"][4], [f"{i}.png" for i in range(nv)])
+        ratio = cc.get_ratio(bench.geometry(wl), 1.0)
+        axs = cc.get_axes(ratio, 1.0, bench.N_CORNERS, sz)
+        if wl["u8"]:
+            src = torch.randint(0, 256, (nv, sz[1], sz[0], 3), dtype=torch.uint8, device=dev)
+        else:
+            src = torch.rand((nv, sz[1], sz[0]), dtype=torch.float32, device=dev)
+        dst = torch.empty_like(src)
+        for coord in coords:
+            for _ in range(a.reps):
+                cc.warp_views(cal, list(range(nv)), src, [ratio] * nv, [axs] * nv, coord=coord, out=dst)
+        torch.cuda.synchronize()
+        del src, dst
 if a.what in ("points", "all"):
     wl = bench.WORKLOADS["c3"]
     cal = cc.Calibration(wl["intr"][:4], [bench.BENCH_VIEW], 1.0, wl["intr"][4], ["extrinsic.png"])

@@ -40,6 +40,14 @@ def run(coord, nviews=64, reps=20):
     return e0.elapsed_time(e1) / reps, host / reps * 1e3
 
 
+# cold call: 64 views nobody has planned yet (host footprints + upload + launch), wall clock
+vcold = [((BV[0][0] - 0.003 * i, BV[0][1] + 0.001 * i, BV[0][2]), (BV[1][0] - 0.02 * i, BV[1][1], BV[1][2] + 0.03 * i)) for i in range(1, 65)]
+calc = cc.Calibration(wl["intr"][:4], vcold, 1.0, wl["intr"][4], [f"c{i}.png" for i in range(64)])
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+cc.warp_views(calc, list(range(64)), src, [ratio] * 64, [axs] * 64, coord="f32", out=dst)
+torch.cuda.synchronize()
+print(f"cold call, 64 new views x 1080p: {(time.perf_counter() - t0) * 1e3:.2f} ms", flush=True)
 SHORT = len(sys.argv) > 1 and sys.argv[1] == "short"
 for coord in ("f32", "f64"):
     for cap in (("",) if SHORT else ("", "1", "2")):
