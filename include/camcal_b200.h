@@ -158,9 +158,12 @@ int cc_rectify_u8c3_host(cc_ctx *ctx, const cc_intr *intr, const cc_view *view,
 /* Frames with DIFFERENT views in one call -- what the reference's plot does: every calibration
  * image is rectified with its own extrinsic, ratio and axes (src/plot_calibration.jl:36-42).
  * Frames [v * frames_per_view, (v+1) * frames_per_view) use views[v], ratios[v] and
- * axs_mins[2v], axs_mins[2v+1].  Device pointers; one launch per view on `stream`, each with its
- * own tile plan (the context caches the 64 most recent).  Frames of one view share the map; a
- * call with one frame per view runs at the single-frame rate. */
+ * axs_mins[2v], axs_mins[2v+1].  Device pointers, ordered on `stream`.  Groups of up to 64 views go
+ * out as ONE launch each (view table in the kernel's parameter space, one staged box size for the
+ * group, tile headers per view; the context caches the plans of the 4 most recent groups and of
+ * the 64 most recent views); a layout the staged kernels cannot take (pitch not a multiple of
+ * 16 bytes, footprints too large to stage) falls back to one launch per view.  Frames of one view
+ * share the map; a call with one frame per view pays the map per frame. */
 int cc_rectify_f32c1_views(cc_ctx *ctx, const cc_intr *intr, const cc_view *views, int nviews,
                            const double *ratios, const int64_t *axs_mins, const float *src,
                            float *dst, int sz1, int sz2, size_t pitch, size_t frame_stride,
