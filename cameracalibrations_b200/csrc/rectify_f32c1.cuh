@@ -244,7 +244,7 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
             const uint32_t R1 = h->R1, R2 = h->R2;
             const uint32_t rel0 = h->base_off;
             m_staged = m_fill = m_skip = 0;
-            if (!EXACT || a_w + kT > g.sz1 || b0 + LPW > g.sz2) {   // partial tile (warp-uniform test; measured: pays only in the exact kernel)
+            if ((!EXACT && !VIEWS) || a_w + kT > g.sz1 || b0 + LPW > g.sz2) {   // partial tile (warp-uniform test; measured: pays only in the exact kernel and with a map per frame)
 #pragma unroll
                 for (int e = 0; e < LPW; ++e)
                     if (a >= g.sz1 || b0 + e >= g.sz2) m_skip |= 1u << e;
@@ -288,10 +288,26 @@ __device__ __forceinline__ void rectify_f32c1_body(const CUtensorMap& tmap, cons
                         const uint32_t l1 = t1[j] - (uint32_t)kMagicBits, l2 = t2[j] - (uint32_t)kMagicBits;
                         const bool st = (l1 < R1) & (l2 < R2);
                         rel[e] = rel0 + l2 * box_pitch_b + l1 * 4u;
-                        // (unconditional: four FSETPs cost less than a divergent branch here; measured)
-                        const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
                         if (st) m_staged |= 1u << e;
-                        if (!inframe) m_fill |= 1u << e;
+                        if (!VIEWS) {
+                            // (unconditional: four FSETPs cost less than a divergent branch here; measured)
+                            const bool inframe = (rr[j] >= 1.0f) & (rr[j] < (float)g.sz1) & (cc_[j] >= 1.0f) & (cc_[j] < (float)g.sz2);
+                            if (!inframe) m_fill |= 1u << e;
+                        }
+                    }
+                }
+                // VIEWS: the map is built per frame, so the fill class (nine instructions per pixel) is worked out
+                // for the warps that need it only -- border tiles, 4 % -- from the same coordinates once more
+                if (VIEWS && !__all_sync(0xffffffffu, m_staged == (1u << LPW) - 1u)) {
+                    ip.x = (float)(gv.axs1 + b0) - pf.c2;
+                    ip.y = ip.x + 1.0f;
+#pragma unroll
+                    for (int hh = 0; hh < LPW / 2; ++hh) {
+                        float2 row, col;
+                        rect_coord2(pf, rtf, ip, row, col);
+                        ip = add2(ip, bc2(2.0f));
+                        if (!((row.x >= 1.0f) & (row.x < (float)g.sz1) & (col.x >= 1.0f) & (col.x < (float)g.sz2))) m_fill |= 1u << (2 * hh);
+                        if (!((row.y >= 1.0f) & (row.y < (float)g.sz1) & (col.y >= 1.0f) & (col.y < (float)g.sz2))) m_fill |= 1u << (2 * hh + 1);
                     }
                 }
             }
