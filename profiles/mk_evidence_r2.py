@@ -84,10 +84,18 @@ W = [("time_us", "gpu__time_duration.sum"), ("dram_rd", "dram__bytes_read.sum"),
      ("lsu_pct", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
      ("l1tex_pct", "l1tex__throughput.avg.pct_of_peak_sustained_active"),
      ("lts_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed"), ("grid", "launch__grid_size"), ("block", "launch__block_size")]
+# a later capture of the views kernels alone (python profiles/prof_kernels.py views --reps 1) replaces their entries
+rep_views = os.path.join(go, "r2_views.ncu-rep")
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if os.path.exists(rep_views):
+        rv = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep_views, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
+        if rv:                                                  # columns matched by name (the two captures may differ)
+            kn, col = hdr.index("Kernel Name"), {h: i for i, h in enumerate(rv[0])}
+            data = [r for r in data if "views_kernel" not in r[kn]] + \
+                   [[r[col[h]] if h in col else "" for h in hdr] for r in rv[2:]]
     ix = {h: i for i, h in enumerate(hdr)}
     seen, traffic = set(), {"source": "ncu --set full --clock-control none, profiles/prof_kernels.py all (r2_all.ncu-rep); dram__bytes_read.sum + dram__bytes_write.sum per launch"}
     tnames = {"rectify_f32c1_kernel<1>": "c2_f64", "rectify_f32c1_kernel<0>": "c2_f32", "rectify_u8c3_kernel<1>": "c3_f64", "rectify_u8c3_kernel<0>": "c3_f32"}
@@ -119,6 +127,8 @@ if os.path.exists(rep):
     # ---- executed-instruction mix and stall reasons of the hot kernels (ncu source page)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
+    if os.path.exists(rep_views):           # the later capture first: the first instance of a kernel wins below
+        rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep_views, "--page", "source", "--csv"], capture_output=True, text=True).stdout))) + rows
     kern, cur, hdr2 = collections.OrderedDict(), None, None
     for r in rows:
         if r and r[0] == "Kernel Name":
