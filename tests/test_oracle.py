@@ -14,6 +14,7 @@ import pytest
 from conftest import load_golden, C2_INTR, SYN_VIEW
 from oracle import oracle_c as oc
 from oracle import oracle_np as on
+from oracle import julia_order as oj
 
 
 def test_cubic_root_known_answers():
@@ -281,3 +282,54 @@ def test_warp_index_selection_vs_cv2_remap():
     # weights quantised to 1/32 px on an image with |gradient| <= 1 per texel: <= 2/32 per axis
     assert err.max() < 4.0 / 32 + 1e-6
     assert err.mean() < 0.02                                        # an off-by-one tap would be ~0.3 on white noise
+
+
+def test_operation_order_sensitivity(example_fit):
+    """How much does the ORDER of the floating-point operations matter?  The CUDA kernels are bit-exact with the C
+    oracle's order (matrix form, explicit fma).  The Julia libraries evaluate the same chain in another order
+    (oracle/julia_order.py: Rodrigues on the vector, no fma).  On the reference's example views and on the bench view
+    of BASELINE configs[1]: coordinates agree to 1e-10 px, NO bilinear tap index differs, no coordinate lies close
+    enough to an integer for ulp-level differences to move a tap, and the fp32 result of the blend differs in at
+    most a few pixels per million, by one ulp."""
+    cases = [(example_fit["intr_tuple"], rv, tv, example_fit["sz"]) for rv, tv in example_fit["view_list"]]
+    cases.append((C2_INTR, (0.05, -0.04, 0.02), (-9.3, -6.4, 30.0), (1080, 1920)))
+    n1, n2 = example_fit["n_corners"]
+    rng = np.random.default_rng(5)
+    tot = diff_px = 0
+    for ci, (intr, rv, tv, sz) in enumerate(cases):
+        ch = oc.chain(intr, rv, tv)
+        if ci < len(example_fit["view_list"]):
+            ip = example_fit["corners_np"][ci].reshape(n2, n1, 2).transpose(1, 0, 2)
+        else:
+            a, b = np.meshgrid(np.arange(20, dtype=np.float64), np.arange(14, dtype=np.float64), indexing="ij")
+            row, col = oc.world2img_soa(ch, a.ravel() * intr[5], b.ravel() * intr[5])
+            ip = np.stack([row, col], axis=-1).reshape(20, 14, 2)
+        ratio = oc.get_ratio(ip, intr[5])
+        axs = oc.get_axes(ratio, intr[5], ip.shape[:2], sz)
+        mr, mc = oc.rectify_map(ch, 1.0 / ratio, axs, sz)          # (sz2, sz1): first axis contiguous
+        mj = oj.rectify_map(intr, rv, tv, 1.0 / ratio, axs, sz)    # (sz1, sz2, 2)
+        jr, jc = mj[..., 0].T, mj[..., 1].T
+        inb = (mr >= 1) & (mr <= sz[0]) & (mc >= 1) & (mc <= sz[1])
+        assert inb.mean() > 0.2
+        assert np.array_equal(inb, (jr >= 1) & (jr <= sz[0]) & (jc >= 1) & (jc <= sz[1])), ci
+        assert max(np.max(np.abs(mr - jr)[inb]), np.max(np.abs(mc - jc)[inb])) < 1e-10, ci
+        assert np.array_equal(np.floor(mr[inb]), np.floor(jr[inb])) and np.array_equal(np.floor(mc[inb]), np.floor(jc[inb])), ci
+        # the only pixels an ulp-level difference could move: coordinates within 1e-9 of an integer
+        near = (np.abs(mr - np.rint(mr)) < 1e-9) | (np.abs(mc - np.rint(mc)) < 1e-9)
+        assert not np.any(near & inb), ci
+        # fp32 blend with both sets of weights (same taps): a rounding boundary is crossed a few times per million
+        img = rng.random((sz[1] + 1, sz[0] + 1)).astype(np.float32).astype(np.float64)
+        def blend(r, c):
+            f1, f2 = np.floor(r[inb]), np.floor(c[inb])
+            f1, f2 = np.where(f1 > sz[0] - 1, f1 - 1, f1), np.where(f2 > sz[1] - 1, f2 - 1, f2)
+            d1, d2 = r[inb] - f1, c[inb] - f2
+            i1, i2 = f1.astype(np.int64) - 1, f2.astype(np.int64) - 1
+            lo = d2 * img[i2 + 1, i1] + (1 - d2) * img[i2, i1]
+            hi = d2 * img[i2 + 1, i1 + 1] + (1 - d2) * img[i2, i1 + 1]
+            return (d1 * hi + (1 - d1) * lo).astype(np.float32)
+        va, vb = blend(mr, mc), blend(jr, jc)
+        ne = va != vb
+        tot += va.size; diff_px += int(ne.sum())
+        if ne.any():
+            assert np.max(np.abs(va[ne].view(np.int32) - vb[ne].view(np.int32))) <= 1, ci
+    assert diff_px / tot < 2e-5
