@@ -312,7 +312,7 @@ void rectify_free_plans(cc_ctx* ctx) {
     }
 }
 
-static void plan_footprints(RectPlan* p) {
+static void plan_footprints(RectPlan* p, bool threads) {
     const ChainD& ch = p->key.ch;
     const RectGeom& g = p->key.g;
     const int tw = p->key.tw, tl = p->key.tl;
@@ -321,9 +321,11 @@ static void plan_footprints(RectPlan* p) {
     p->n2 = (g.sz2 + tl - 1) / tl;
     p->origin.assign((size_t)p->n1 * p->n2 * 2, -4);
     p->p3_ok.assign((size_t)p->n1 * p->n2, 1);
+    // strips [s0, s1) of the plan; partial maxima / tilt votes of the range go to out[3]
+    auto strips = [&](int s0, int s1, long long* out) {
     int m1 = 0, m2 = 0;
     long long tilt = 0;
-    for (int t1 = 0; t1 < p->n1; ++t1) {
+    for (int t1 = s0; t1 < s1; ++t1) {
         const int a_lo = t1 * tw, a_hi = std::min(a_lo + tw - 1, g.sz1 - 1);
         for (int t2 = 0; t2 < p->n2; ++t2) {
             const int b_lo = t2 * tl, b_hi = std::min(b_lo + tl - 1, g.sz2 - 1);
@@ -372,6 +374,27 @@ static void plan_footprints(RectPlan* p) {
             m2 = std::max(m2, (int)(std::floor(cmax) - std::floor(cmin)));
         }
     }
+    out[0] = m1; out[1] = m2; out[2] = tilt;
+    };
+    // large plans (a 4K frame has 8160 tiles x 36 coordinate evaluations) are split over host threads; every
+    // tile writes its own slots of origin / p3_ok, the partials are combined in strip order
+    const long long tiles = (long long)p->n1 * p->n2;
+    const int nt = !threads ? 1 : (int)std::max(1ll, std::min<long long>({tiles / 512, 16ll, (long long)std::max(1u, std::thread::hardware_concurrency()), (long long)p->n1}));
+    std::vector<long long> part((size_t)nt * 3, 0);
+    if (nt == 1) {
+        strips(0, p->n1, part.data());
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) {
+            const int s0 = (int)((long long)p->n1 * t / nt), s1 = (int)((long long)p->n1 * (t + 1) / nt);
+            if (t + 1 < nt) th.emplace_back(strips, s0, s1, part.data() + 3 * t);
+            else strips(s0, s1, part.data() + 3 * t);
+        }
+        for (auto& x : th) x.join();
+    }
+    int m1 = 0, m2 = 0;
+    long long tilt = 0;
+    for (int t = 0; t < nt; ++t) { m1 = std::max(m1, (int)part[3 * t]); m2 = std::max(m2, (int)part[3 * t + 1]); tilt += part[3 * t + 2]; }
     // taps floor-1 .. floor; 2 texels of slack below (origin) and 1 above
     p->need1 = m1 + 2 + 3;
     p->need2 = m2 + 2 + 3;
@@ -506,13 +529,14 @@ static RectPlan* plan_find(cc_ctx* ctx, const PlanKey& key) {
     return nullptr;
 }
 
-// footprints, box and headers of one parameter set: host arithmetic only (safe to run on several threads)
-static RectPlan* plan_build(const PlanKey& key) {
+// footprints, box and headers of one parameter set: host arithmetic only (safe to run on several threads;
+// threads: split a large plan over host threads itself -- off when the caller already runs one plan per thread)
+static RectPlan* plan_build(const PlanKey& key, bool threads) {
     RectPlan* p = new (std::nothrow) RectPlan();
     if (!p) return nullptr;
     p->key = key; p->d_hdr = nullptr; p->d_q2 = nullptr;
     p->per_sm[0] = p->per_sm[1] = 0; p->per_sm_smem[0] = p->per_sm_smem[1] = 0;
-    plan_footprints(p);
+    plan_footprints(p, threads);
     plan_boxes(p);
     return p;
 }
@@ -539,7 +563,7 @@ static RectPlan* plan_get(cc_ctx* ctx, const ChainD& ch, double ratio, const Rec
                           int pxb, cudaStream_t st) {
     const PlanKey key = plan_key(ch, ratio, g, tw, tl, pxb);
     if (RectPlan* p = plan_find(ctx, key)) return plan_upload(p, st) ? p : nullptr;
-    RectPlan* p = plan_build(key);
+    RectPlan* p = plan_build(key, true);
     if (!p) return nullptr;
     if (!plan_upload(p, st)) {
         plan_free(p);
@@ -859,7 +883,7 @@ static MultiPlan* multi_get(cc_ctx* ctx, const ChainD* chs, const double* ratios
     if (!missing.empty()) {
         const int nt = (int)std::min<size_t>(missing.size(), std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
         std::vector<std::thread> th;
-        auto work = [&](int t) { for (size_t i = (size_t)t; i < missing.size(); i += (size_t)nt) pl[missing[i]] = plan_build(keys[missing[i]]); };
+        auto work = [&](int t) { for (size_t i = (size_t)t; i < missing.size(); i += (size_t)nt) pl[missing[i]] = plan_build(keys[missing[i]], nt == 1); };
         for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
         work(0);
         for (auto& x : th) x.join();
