@@ -387,8 +387,12 @@ static void plan_footprints(RectPlan* p, bool threads) {
         std::vector<std::thread> th;
         for (int t = 0; t < nt; ++t) {
             const int s0 = (int)((long long)p->n1 * t / nt), s1 = (int)((long long)p->n1 * (t + 1) / nt);
-            if (t + 1 < nt) th.emplace_back(strips, s0, s1, part.data() + 3 * t);
-            else strips(s0, s1, part.data() + 3 * t);
+            bool spawned = false;
+            if (t + 1 < nt) {
+                try { th.emplace_back(strips, s0, s1, part.data() + 3 * t); spawned = true; }
+                catch (...) {}                  // no thread to be had: this range runs here (nothing throws across the C ABI)
+            }
+            if (!spawned) strips(s0, s1, part.data() + 3 * t);
         }
         for (auto& x : th) x.join();
     }
@@ -884,7 +888,10 @@ static MultiPlan* multi_get(cc_ctx* ctx, const ChainD* chs, const double* ratios
         const int nt = (int)std::min<size_t>(missing.size(), std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
         std::vector<std::thread> th;
         auto work = [&](int t) { for (size_t i = (size_t)t; i < missing.size(); i += (size_t)nt) pl[missing[i]] = plan_build(keys[missing[i]], nt == 1); };
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        for (int t = 1; t < nt; ++t) {
+            try { th.emplace_back(work, t); }
+            catch (...) { work(t); }            // no thread to be had: this share runs here
+        }
         work(0);
         for (auto& x : th) x.join();
     }
